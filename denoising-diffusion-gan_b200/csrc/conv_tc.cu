@@ -1,0 +1,731 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores with TMEM accumulators (sm_100a).
+//
+// Replaces the cuDNN convolutions the reference reaches through nn.Conv2d / F.conv2d
+// (score_sde/models/layers.py:114-138, dense_layer.py:73-80, up_or_down_sampling.py:56,183,
+//  NIN at layers.py:489-512) together with the elementwise work around them
+// (AdaGN scale/shift + SiLU at layerspp.py:279,300; "+= Dense_0(temb)" :298-299; the 1x1 skip conv
+//  and "(x + h)/sqrt(2)" :305-310; LeakyReLU at discriminator.py:78-82; tanh at ncsnpp...:428).
+//
+// GEMM view: D[M = pixels][N = Cout] += A[M][K = taps*Cin] * B[K][N].
+//   * A (activations) is produced in shared memory by the producer warps: fp32 NHWC rows are loaded from HBM,
+//     the fused prologue y = act(scale[n,c]*x + shift[n,c]) is applied, and the result is split into
+//     bf16 hi + bf16 lo planes ("BF16x3": Ahi*Bhi + Alo*Bhi + Ahi*Blo with fp32 accumulation reproduces fp32
+//     convolution to ~5e-6 relative L2, SURVEY.md section 7 hard part 1).
+//     Layout: [chunk of 8 channels][window row][8 x bf16] = the UMMA K-major SWIZZLE_NONE canonical layout with
+//     SBO = 128 B (8 rows x 16 B, rows contiguous) and LBO = window pitch.  Because rows are exactly 16 B apart,
+//     a filter tap (dr, ds) is just a start-address offset of (dr*Wp + ds)*16 B into the same window: the 3x3
+//     convolution runs over the zero-padded linear pixel space [N][H+2][W+2] and border outputs are discarded.
+//   * B (weights) is pre-packed on the device (ddg_conv_pack_weights) into per-stage blobs that are already the
+//     shared-memory image; the TMA engine (cp.async.bulk, 1-D) streams them through a ring of mbarrier stages.
+//   * D lives in TMEM (MSUB accumulators of 128 lanes x NT fp32 columns); one elected thread issues
+//     tcgen05.mma.cta_group::1.kind::f16; tcgen05.commit releases the smem stages and signals the epilogue.
+//   * Epilogue: tcgen05.ld -> + bias[c] + addvec[n,c] -> (+ residual) * out_scale -> act -> store (padded NHWC /
+//     NHWC / NCHW) and per-(n,c) sum / sum-of-squares accumulation for the GroupNorm that consumes the output.
+#include "common.cuh"
+#include "ddgan_b200.h"
+
+namespace ddg {
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, SWIZZLE_NONE, version 1 (Blackwell).  Offsets in bytes (multiples of 16).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Kernel parameters (device view)
+// ---------------------------------------------------------------------------------------------------------
+struct SrcDev {
+  const float* x;
+  const float* scale;
+  const float* shift;
+  int C;          // channels of the source tensor (row pitch)
+  int act;
+  int ntaps;
+  int padded;     // gather mode only: source is padded NHWC
+  int tapoff[9];  // window mode: row offset of each tap relative to the window start
+};
+
+struct ConvDev {
+  SrcDev src[DDG_CONV_MAX_SRC];
+  int nsrc;
+  const __nv_bfloat16* wpack;  // [n_tile][stage][blob]
+  int window;                  // 1: padded-linear window mode, 0: gather (pure 1x1)
+  int N, Hp, Wp;               // window mode: padded input space
+  int Hout, Wout;              // output image size
+  int Mtotal;                  // rows of the M space
+  int Cout;                    // real output channels
+  int total_stages;            // B stages per n-tile
+  int win_rows;                // rows in the A window (incl. margins)
+  int win_pitch;               // LBO of A in bytes
+  int margin;                  // rows before the first output row in the window
+  const float* bias;
+  const float* addvec;
+  int addvec_stride;
+  const float* res;
+  float out_scale;
+  int out_act;
+  float* out;
+  int out_mode;                // 0 padded NHWC, 1 NHWC, 2 NCHW
+  int out_C;                   // channel pitch of out / res (NHWC modes)
+  double* stats;               // [N][Cout][2] or null
+  int swap_lbo_sbo;            // debug
+  int batch_rows;              // >0: batched GEMM mode (gather only): blockIdx.z = batch, rows per batch
+  long w_batch_stride;         // bytes between the packed B operands of consecutive batches
+};
+
+constexpr int kProdWarps = 8;
+constexpr int kThreads = (kProdWarps + 2) * 32;
+
+template <int MSUB, int NT, int KB, int PREC>
+struct ConvCfg {
+  static constexpr int MT = 128 * MSUB;
+  static constexpr int KCH = KB / 8;                              // 16-byte chunks along K per row
+  static constexpr int NPL = (PREC == 3) ? 2 : 1;                 // operand planes (hi, lo)
+  static constexpr int B_PLANE = KB * NT * 2;                     // bytes of one B plane per stage
+  static constexpr int B_STAGE = B_PLANE * NPL;
+  static constexpr int NSB = (B_STAGE <= 8192) ? 6 : (B_STAGE <= 16384 ? 4 : 3);
+  static constexpr int TMEM_COLS = (MSUB * NT <= 32) ? 32 : (MSUB * NT <= 64 ? 64 : (MSUB * NT <= 128 ? 128 : (MSUB * NT <= 256 ? 256 : 512)));
+};
+
+__device__ __forceinline__ void decode_out_row(const ConvDev& p, int m, int m_end, bool& valid, int& n, int& h, int& w) {
+  if (p.window) {
+    int img = p.Hp * p.Wp;
+    n = m / img;
+    int r = m - n * img;
+    int hp = r / p.Wp;
+    int wp = r - hp * p.Wp;
+    h = hp - 1;
+    w = wp - 1;
+    valid = (m < p.Mtotal) && (h >= 0) && (h < p.Hout) && (w >= 0) && (w < p.Wout);
+  } else {
+    int img = p.Hout * p.Wout;
+    n = m / img;
+    int r = m - n * img;
+    h = r / p.Wout;
+    w = r - h * p.Wout;
+    valid = m < m_end;
+  }
+  if (n >= p.N) n = p.N - 1;
+}
+
+template <int MSUB, int NT, int KB, int PREC>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvDev p) {
+  using Cfg = ConvCfg<MSUB, NT, KB, PREC>;
+  constexpr int MT = Cfg::MT;
+  constexpr int KCH = Cfg::KCH;
+  constexpr int NPL = Cfg::NPL;
+  constexpr int NSB = Cfg::NSB;
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  // carve: barriers | tmem ptr | B ring | A ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto fullA = [&](int s) { return bar_base + 8u * s; };
+  auto emptyA = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto fullB = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto emptyB = [&](int s) { return bar_base + 8u * (4 + NSB + s); };
+  const uint32_t accFull = bar_base + 8u * (4 + 2 * NSB);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (5 + 2 * NSB));
+  uint8_t* sB = smem + 256;
+  const int a_plane = KCH * p.win_pitch;          // bytes of one A plane
+  const int a_stage = a_plane * NPL;
+  uint8_t* sA = sB + NSB * Cfg::B_STAGE;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = (p.batch_rows > 0 ? blockIdx.z * p.batch_rows : 0) + blockIdx.x * MT;
+  const int m_end = p.batch_rows > 0 ? (blockIdx.z + 1) * p.batch_rows : p.Mtotal;
+  const int ntile = blockIdx.y;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(fullA(s), kProdWarps * 32); mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < NSB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
+    mbar_init(accFull, 1);
+    fence_barrier_init();
+  }
+  if (warp == kProdWarps + 1) {
+    tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // number of K blocks
+  int nkb_total = 0;
+  for (int s = 0; s < p.nsrc; ++s) nkb_total += p.src[s].C / KB;
+
+  if (warp < kProdWarps) {
+    // =================================== A producers ===================================
+    const int tid = threadIdx.x;                     // 0..255
+    constexpr int NPT = kProdWarps * 32;
+    const int c = tid % KCH;                         // fixed 16-byte chunk of this thread
+    const int e0 = tid / KCH;
+    constexpr int ESTEP = NPT / KCH;
+    int kb_idx = 0;
+    for (int s = 0; s < p.nsrc; ++s) {
+      const SrcDev& S = p.src[s];
+      const bool has_affine = (S.scale != nullptr);
+      // rows of the window actually needed by this source
+      int row_lo = 0, row_hi = p.win_rows;
+      if (p.window && S.ntaps == 1) { row_lo = S.tapoff[0]; row_hi = S.tapoff[0] + MT; }
+      for (int kb = 0; kb < S.C / KB; ++kb, ++kb_idx) {
+        const int st = kb_idx & 1;
+        const uint32_t ph = (kb_idx >> 1) & 1;
+        mbar_wait(emptyA(st), ph ^ 1);
+        uint8_t* dst_hi = sA + st * a_stage + c * p.win_pitch;
+        uint8_t* dst_lo = dst_hi + a_plane;
+        const int ch0 = kb * KB + c * 8;
+        int cur_n = -1;
+        float sc[8], sh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; }
+        for (int e = row_lo + e0; e < row_hi; e += ESTEP) {
+          float v[8];
+          bool live = false;
+          int n = 0;
+          const float* src = nullptr;
+          if (p.window) {
+            const int g = m0 - p.margin + e;         // row in padded linear space
+            if (g >= 0 && g < p.Mtotal) {
+              const int img = p.Hp * p.Wp;
+              n = g / img;
+              if (has_affine) {                      // padding must stay zero after the affine prologue
+                const int r = g - n * img;
+                const int hp = r / p.Wp, wp = r - hp * p.Wp;
+                live = (hp >= 1) && (hp < p.Hp - 1) && (wp >= 1) && (wp < p.Wp - 1);
+              } else {
+                live = true;
+              }
+              src = S.x + (size_t)g * S.C + ch0;
+            }
+          } else {
+            const int m = m0 + e;
+            if (m < m_end) {
+              live = true;
+              const int img = p.Hout * p.Wout;
+              n = m / img;
+              if (S.padded) {
+                const int r = m - n * img;
+                const int h = r / p.Wout, w = r - h * p.Wout;
+                src = S.x + ((size_t)(n * (p.Hout + 2) + h + 1) * (p.Wout + 2) + (w + 1)) * S.C + ch0;
+              } else {
+                src = S.x + (size_t)m * S.C + ch0;
+              }
+            }
+          }
+          if (live) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            if (has_affine) {
+              if (n != cur_n) {
+                cur_n = n;
+                const float4* ps = reinterpret_cast<const float4*>(S.scale + (size_t)n * S.C + ch0);
+                const float4* pt = reinterpret_cast<const float4*>(S.shift + (size_t)n * S.C + ch0);
+                float4 s0 = __ldg(ps), s1 = __ldg(ps + 1), t0 = __ldg(pt), t1 = __ldg(pt + 1);
+                sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+                sh[0] = t0.x; sh[1] = t0.y; sh[2] = t0.z; sh[3] = t0.w; sh[4] = t1.x; sh[5] = t1.y; sh[6] = t1.z; sh[7] = t1.w;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+            }
+            if (S.act == ACT_SILU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+            } else if (S.act == ACT_LEAKY) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = leaky_f(v[j]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = 0.f;
+          }
+          uint4 hi, lo;
+          split_bf16x2(v[0], v[1], hi.x, lo.x);
+          split_bf16x2(v[2], v[3], hi.y, lo.y);
+          split_bf16x2(v[4], v[5], hi.z, lo.z);
+          split_bf16x2(v[6], v[7], hi.w, lo.w);
+          *reinterpret_cast<uint4*>(dst_hi + e * 16) = hi;
+          if (NPL == 2) *reinterpret_cast<uint4*>(dst_lo + e * 16) = lo;
+        }
+        fence_proxy_async();
+        mbar_arrive(fullA(st));
+      }
+    }
+
+    // =================================== epilogue ===================================
+    mbar_wait(accFull, 0);
+    tc_fence_after();
+    const int quad = warp & 3;                       // TMEM lane quadrant accessible by this warp
+    const int half = warp >> 2;                      // column half handled by this warp
+    constexpr int CW = (NT >= 64) ? 32 : 16;         // columns per tcgen05.ld
+    constexpr int NCHUNK = NT / CW;
+    for (int sub = 0; sub < MSUB; ++sub) {
+      const int m = m0 + sub * 128 + quad * 32 + lane;
+      bool valid; int n, h, w;
+      decode_out_row(p, m, m_end, valid, n, h, w);
+      size_t obase = 0;
+      if (p.out_mode == 0) obase = ((size_t)(n * (p.Hout + 2) + h + 1) * (p.Wout + 2) + (w + 1)) * p.out_C;
+      else if (p.out_mode == 1) obase = ((size_t)(n * p.Hout + h) * p.Wout + w) * p.out_C;
+      const int n_first = __shfl_sync(0xffffffffu, n, 0);
+      const int n_last = __shfl_sync(0xffffffffu, n, 31);
+      for (int ck = half; ck < NCHUNK; ck += 2) {
+        const int col0 = ntile * NT + ck * CW;
+        float v[CW];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(sub * NT + ck * CW);
+        if (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+        tmem_ld_wait();
+        if (col0 < p.Cout) {
+#pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            const int cc = col0 + j;
+            float y = v[j];
+            if (cc < p.Cout) {
+              if (p.bias) y += __ldg(p.bias + cc);
+              if (p.addvec) y += __ldg(p.addvec + (size_t)n * p.addvec_stride + cc);
+            }
+            v[j] = y;
+          }
+          if (valid) {
+            if (p.out_mode != 2) {
+              if (p.res) {
+                const float4* r4 = reinterpret_cast<const float4*>(p.res + obase + col0);
+#pragma unroll
+                for (int j = 0; j < CW / 4; ++j) {
+                  const float4 r = __ldg(r4 + j);
+                  v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < CW; ++j) v[j] = apply_act(v[j] * p.out_scale, p.out_act);
+              float4* o4 = reinterpret_cast<float4*>(p.out + obase + col0);
+#pragma unroll
+              for (int j = 0; j < CW / 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) {
+                const int cc = col0 + j;
+                if (cc < p.Cout) {
+                  const size_t oi = ((size_t)(n * p.Cout + cc) * p.Hout + h) * p.Wout + w;
+                  float y = v[j];
+                  if (p.res) y += __ldg(p.res + oi);
+                  y = apply_act(y * p.out_scale, p.out_act);
+                  v[j] = y;
+                  p.out[oi] = y;
+                }
+              }
+            }
+          }
+          if (p.stats) {
+            // per-(n, channel) sum and sum of squares of the stored values; lanes = rows, registers = channels.
+            for (int pass = 0; pass < 2; ++pass) {
+              const int n_sel = pass == 0 ? n_first : n_last;
+              if (pass == 1 && n_last == n_first) break;
+              const bool mine = valid && (n == n_sel);
+              float s1[CW], s2[CW];
+#pragma unroll
+              for (int j = 0; j < CW; ++j) { const float y = mine ? v[j] : 0.f; s1[j] = y; s2[j] = y * y; }
+              // transpose-reduce over the 32 lanes: afterwards lane L holds column (L % CW) totals in s1[0]/s2[0]
+#pragma unroll
+              for (int sft = 16; sft >= 1; sft >>= 1) {
+                if (sft < CW) {
+                  const bool up = (lane & sft) != 0;
+#pragma unroll
+                  for (int i = 0; i < sft; ++i) {
+                    const float a1 = up ? s1[i] : s1[i + sft];
+                    const float b1 = up ? s1[i + sft] : s1[i];
+                    s1[i] = b1 + __shfl_xor_sync(0xffffffffu, a1, sft);
+                    const float a2 = up ? s2[i] : s2[i + sft];
+                    const float b2 = up ? s2[i + sft] : s2[i];
+                    s2[i] = b2 + __shfl_xor_sync(0xffffffffu, a2, sft);
+                  }
+                } else {
+                  // CW == 16 and sft == 16: plain butterfly add of all 16 columns
+#pragma unroll
+                  for (int i = 0; i < CW; ++i) {
+                    s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], sft);
+                    s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], sft);
+                  }
+                }
+              }
+              const int cc = col0 + (lane % CW);
+              if (cc < p.Cout && (CW == 32 || lane < 16)) {
+                double* dst = p.stats + ((size_t)n_sel * p.Cout + cc) * 2;
+                atomicAdd(dst, (double)s1[0]);
+                atomicAdd(dst + 1, (double)s2[0]);
+              }
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == kProdWarps) {
+    // =================================== weight loader (TMA bulk) ===================================
+    if (lane == 0) {
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)ntile * p.total_stages * Cfg::B_STAGE +
+                            (p.batch_rows > 0 ? (size_t)blockIdx.z * p.w_batch_stride : 0);
+      for (int i = 0; i < p.total_stages; ++i) {
+        const int st = i % NSB;
+        const uint32_t ph = (i / NSB) & 1;
+        mbar_wait(emptyB(st), ph ^ 1);
+        mbar_arrive_expect_tx(fullB(st), Cfg::B_STAGE);
+        tma_bulk_g2s(smem_u32(sB + st * Cfg::B_STAGE), wsrc + (size_t)i * Cfg::B_STAGE, Cfg::B_STAGE, fullB(st));
+      }
+    }
+    __syncwarp();
+  } else {
+    // =================================== MMA issuer ===================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t a_lbo = p.swap_lbo_sbo ? 128u : (uint32_t)p.win_pitch;
+      const uint32_t a_sbo = p.swap_lbo_sbo ? (uint32_t)p.win_pitch : 128u;
+      const uint32_t b_lbo = p.swap_lbo_sbo ? 128u : (uint32_t)(NT * 16);
+      const uint32_t b_sbo = p.swap_lbo_sbo ? (uint32_t)(NT * 16) : 128u;
+      int kb_idx = 0, bi = 0;
+      uint32_t acc = 0;
+      for (int s = 0; s < p.nsrc; ++s) {
+        const SrcDev& S = p.src[s];
+        for (int kb = 0; kb < S.C / KB; ++kb, ++kb_idx) {
+          const int stA = kb_idx & 1;
+          mbar_wait(fullA(stA), (kb_idx >> 1) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(sA + stA * a_stage);
+          const uint32_t a_lo = a_hi + a_plane;
+          for (int t = 0; t < S.ntaps; ++t, ++bi) {
+            const int stB = bi % NSB;
+            mbar_wait(fullB(stB), (bi / NSB) & 1);
+            tc_fence_after();
+            const uint32_t b_hi = smem_u32(sB + stB * Cfg::B_STAGE);
+            const uint32_t b_lo = b_hi + Cfg::B_PLANE;
+            const uint32_t toff = (uint32_t)(p.window ? S.tapoff[t] : 0) * 16u;
+#pragma unroll
+            for (int sub = 0; sub < MSUB; ++sub) {
+              const uint32_t d = tmem_base + (uint32_t)(sub * NT);
+              uint32_t acc_s = acc;
+#pragma unroll
+              for (int kk = 0; kk < KB / 16; ++kk) {
+                const uint32_t aoff = toff + (uint32_t)(sub * 128 * 16) + (uint32_t)(kk * 2) * (uint32_t)p.win_pitch;
+                const uint32_t boff = (uint32_t)(kk * 2) * (uint32_t)(NT * 16);
+                const uint64_t dah = make_smem_desc(a_hi + aoff, a_lbo, a_sbo);
+                const uint64_t dbh = make_smem_desc(b_hi + boff, b_lbo, b_sbo);
+                if (PREC == 3) {
+                  const uint64_t dal = make_smem_desc(a_lo + aoff, a_lbo, a_sbo);
+                  const uint64_t dbl = make_smem_desc(b_lo + boff, b_lbo, b_sbo);
+                  umma_bf16(d, dal, dbh, idesc, acc_s);
+                  umma_bf16(d, dah, dbl, idesc, 1u);
+                  umma_bf16(d, dah, dbh, idesc, 1u);
+                } else {
+                  umma_bf16(d, dah, dbh, idesc, acc_s);
+                }
+                acc_s = 1u;
+              }
+            }
+            acc = 1u;
+            umma_commit(emptyB(stB));
+          }
+          umma_commit(emptyA(stA));
+        }
+      }
+      umma_commit(accFull);
+    }
+    __syncwarp();
+  }
+
+  __syncthreads();
+  if (warp == kProdWarps + 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Weight packing: fp32 weights (arbitrary strides) -> per-(n-tile, stage) shared-memory images, bf16 hi [+ lo].
+// Blob layout per stage: plane hi then plane lo; plane = [KB/8 chunks][NT rows][8 k] bf16.
+// ---------------------------------------------------------------------------------------------------------
+template <int PREC>
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin_real,
+                                    int Cin_pad, int ntaps, long s_co, long s_ci, long s_tap, int flip_taps, int NT, int KB,
+                                    int n_tiles, int stage_offset, int total_stages, long w_batch_stride, long out_batch_stride) {
+  // one thread per 16-byte chunk: (ntile, kb, tap, chunk, row); blockIdx.y = batch (per-image operands of the attention GEMMs)
+  w += (long)blockIdx.y * w_batch_stride;
+  out += (long)blockIdx.y * out_batch_stride;
+  const int KCH = KB / 8;
+  const long per_stage = (long)KCH * NT;
+  const int nkb = Cin_pad / KB;
+  const long total = (long)n_tiles * nkb * ntaps * per_stage;
+  const long plane_elems = (long)KB * NT;
+  const int npl = (PREC == 3) ? 2 : 1;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i;
+    const int row = r % NT; r /= NT;
+    const int ch = r % KCH; r /= KCH;
+    const int tap = r % ntaps; r /= ntaps;
+    const int kb = r % nkb; r /= nkb;
+    const int nt = (int)r;
+    const int co = nt * NT + row;
+    const int tsrc = flip_taps ? (ntaps - 1 - tap) : tap;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = 0.f, b = 0.f;
+      const int ci = kb * KB + ch * 8 + 2 * j;
+      if (co < Cout) {
+        if (ci < Cin_real) a = w[co * s_co + ci * s_ci + tsrc * s_tap];
+        if (ci + 1 < Cin_real) b = w[co * s_co + (ci + 1) * s_ci + tsrc * s_tap];
+      }
+      split_bf16x2(a, b, hi[j], lo[j]);
+    }
+    const long stage = stage_offset + (long)kb * ntaps + tap;
+    __nv_bfloat16* blob = out + ((long)nt * total_stages + stage) * plane_elems * npl;
+    uint4* dh = reinterpret_cast<uint4*>(blob + ((long)ch * NT + row) * 8);
+    *dh = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (PREC == 3) {
+      uint4* dl = reinterpret_cast<uint4*>(blob + plane_elems + ((long)ch * NT + row) * 8);
+      *dl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------------------
+struct Variant { int msub, nt, kb; };
+
+static int pick_nt(int cout) {
+  if (cout <= 16) return 16;
+  if (cout <= 64) return 64;
+  return 128;
+}
+
+template <int MSUB, int NT, int KB, int PREC>
+static int launch_conv(const ConvDev& d, int n_tiles, cudaStream_t stream) {
+  using Cfg = ConvCfg<MSUB, NT, KB, PREC>;
+  const size_t smem = 256 + (size_t)Cfg::NSB * Cfg::B_STAGE + 2 * (size_t)Cfg::NPL * Cfg::KCH * d.win_pitch;
+  if (smem > 227 * 1024) { ddg_set_last_error("conv_tc: shared memory budget exceeded"); return DDG_ERR_UNSUPPORTED; }
+  auto kern = conv_tc_kernel<MSUB, NT, KB, PREC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  dim3 grid((d.Mtotal + Cfg::MT - 1) / Cfg::MT, n_tiles);
+  if (d.batch_rows > 0) grid = dim3((d.batch_rows + Cfg::MT - 1) / Cfg::MT, n_tiles, d.Mtotal / d.batch_rows);
+  kern<<<grid, kThreads, smem, stream>>>(d);
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}
+
+}  // namespace ddg
+
+using namespace ddg;
+
+extern "C" int ddg_conv_tile_n(int cout) { return pick_nt(cout); }
+
+extern "C" long ddg_conv_packed_bytes(int cout, int total_stages, int kb, int precision) {
+  const int nt = pick_nt(cout);
+  const int n_tiles = (cout + nt - 1) / nt;
+  return (long)n_tiles * total_stages * kb * nt * 2 * (precision == 3 ? 2 : 1);
+}
+
+extern "C" int ddg_conv_pack_weights(const float* w, void* out, int cout, int cin_real, int cin_pad, int ntaps, long s_co,
+                                     long s_ci, long s_tap, int flip_taps, int kb, int stage_offset, int total_stages,
+                                     int precision, int batch, long w_batch_stride, cudaStream_t stream) {
+  if (!w || !out || cin_pad % kb != 0 || (kb != 32 && kb != 64)) { ddg_set_last_error("pack_weights: bad args"); return DDG_ERR_ARG; }
+  const int nt = pick_nt(cout);
+  const int n_tiles = (cout + nt - 1) / nt;
+  const long total = (long)n_tiles * (cin_pad / kb) * ntaps * (kb / 8) * nt;
+  const int threads = 256;
+  const int blocks = (int)((total + threads - 1) / threads < 148 * 16 ? (total + threads - 1) / threads : 148 * 16);
+  if (batch < 1) batch = 1;
+  const long out_bs = ddg_conv_packed_bytes(cout, total_stages, kb, precision) / 2;  // in bf16 elements
+  dim3 grid(blocks, batch);
+  if (precision == 3)
+    pack_weights_kernel<3><<<grid, threads, 0, stream>>>(w, (__nv_bfloat16*)out, cout, cin_real, cin_pad, ntaps, s_co, s_ci,
+                                                        s_tap, flip_taps, nt, kb, n_tiles, stage_offset, total_stages, w_batch_stride, out_bs);
+  else
+    pack_weights_kernel<1><<<grid, threads, 0, stream>>>(w, (__nv_bfloat16*)out, cout, cin_real, cin_pad, ntaps, s_co, s_ci,
+                                                        s_tap, flip_taps, nt, kb, n_tiles, stage_offset, total_stages, w_batch_stride, out_bs);
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}
+
+extern "C" int ddg_conv2d_fwd(const ddg_conv_desc* c, cudaStream_t stream) {
+  if (!c || c->nsrc < 1 || c->nsrc > DDG_CONV_MAX_SRC || !c->out || !c->wpack) { ddg_set_last_error("conv2d_fwd: bad args"); return DDG_ERR_ARG; }
+  const int KB = c->kb;
+  if (KB != 32) { ddg_set_last_error("conv2d_fwd: kb must be 32"); return DDG_ERR_UNSUPPORTED; }
+  ConvDev d{};
+  d.nsrc = c->nsrc;
+  bool window = false;
+  int total_stages = 0;
+  for (int s = 0; s < c->nsrc; ++s) {
+    const ddg_conv_src& S = c->src[s];
+    if (!S.x || S.C % KB != 0 || S.ntaps < 1 || S.ntaps > 9) { ddg_set_last_error("conv2d_fwd: bad source"); return DDG_ERR_ARG; }
+    if ((S.scale == nullptr) != (S.shift == nullptr)) { ddg_set_last_error("conv2d_fwd: scale/shift must come together"); return DDG_ERR_ARG; }
+    if (S.ntaps > 1) window = true;
+    total_stages += (S.C / KB) * S.ntaps;
+  }
+  d.window = window ? 1 : 0;
+  d.N = c->N; d.Hout = c->Hout; d.Wout = c->Wout;
+  d.Hp = c->Hp; d.Wp = c->Wp;
+  if (window) {
+    if (d.Hp < d.Hout + 2 || d.Wp < d.Wout + 2) { ddg_set_last_error("conv2d_fwd: padded dims too small"); return DDG_ERR_ARG; }
+    d.Mtotal = d.N * d.Hp * d.Wp;
+    d.margin = d.Wp + 1;
+  } else {
+    d.Mtotal = d.N * d.Hout * d.Wout;
+    d.margin = 0;
+  }
+  for (int s = 0; s < c->nsrc; ++s) {
+    const ddg_conv_src& S = c->src[s];
+    SrcDev& D = d.src[s];
+    D.x = S.x; D.scale = S.scale; D.shift = S.shift; D.C = S.C; D.act = S.act; D.ntaps = S.ntaps; D.padded = S.padded;
+    for (int t = 0; t < S.ntaps; ++t) {
+      if (window) {
+        if (!S.padded) { ddg_set_last_error("conv2d_fwd: window mode needs padded sources"); return DDG_ERR_ARG; }
+        D.tapoff[t] = d.margin + S.tap_dr[t] * d.Wp + S.tap_ds[t];
+      } else {
+        D.tapoff[t] = 0;
+      }
+    }
+  }
+  d.wpack = (const __nv_bfloat16*)c->wpack;
+  d.Cout = c->Cout;
+  d.total_stages = total_stages;
+  d.bias = c->bias; d.addvec = c->addvec; d.addvec_stride = c->addvec_stride;
+  d.res = c->res; d.out_scale = c->out_scale; d.out_act = c->out_act;
+  d.out = c->out; d.out_mode = c->out_mode; d.out_C = c->out_C > 0 ? c->out_C : c->Cout;
+  d.stats = c->stats;
+  d.swap_lbo_sbo = c->debug_swap_lbo_sbo;
+  d.batch_rows = 0;
+  d.w_batch_stride = 0;
+  if (c->batch_rows > 0) {
+    if (window || d.Mtotal % c->batch_rows != 0) { ddg_set_last_error("conv2d_fwd: batched mode needs a 1x1 problem with Mtotal % batch_rows == 0"); return DDG_ERR_ARG; }
+    d.batch_rows = c->batch_rows;
+    d.w_batch_stride = ddg_conv_packed_bytes(c->Cout, total_stages, KB, c->precision == 1 ? 1 : 3);
+  }
+  if (d.out_mode != 2 && (d.out_C % 4 != 0)) { ddg_set_last_error("conv2d_fwd: NHWC output pitch must be a multiple of 4"); return DDG_ERR_ARG; }
+
+  const int nt = pick_nt(c->Cout);
+  const int n_tiles = (c->Cout + nt - 1) / nt;
+  if (d.out_mode != 2 && (c->Cout % (nt >= 64 ? 32 : 16) != 0)) { ddg_set_last_error("conv2d_fwd: Cout must be a multiple of the epilogue chunk for NHWC output"); return DDG_ERR_UNSUPPORTED; }
+  // M sub-tiles: two accumulators per CTA when the grid still fills the machine
+  int msub = c->msub;
+  if (msub == 0) {
+    const long tiles2 = ((long)d.Mtotal + 255) / 256 * n_tiles;
+    msub = (tiles2 >= 2 * 148) ? 2 : 1;
+    if (d.batch_rows > 0 && d.batch_rows % 256 != 0) msub = 1;
+  }
+  const int MT = 128 * msub;
+  int rows = window ? MT + 2 * d.margin : MT;
+  if ((rows & 1) == 0) rows += 1;                   // odd pitch (in 16-byte units): conflict-free chunk-strided stores
+  d.win_rows = window ? MT + 2 * d.margin : MT;
+  d.win_pitch = rows * 16;
+  const int prec = c->precision == 1 ? 1 : 3;
+
+#define DDG_LAUNCH(MS, NTV, PR) return launch_conv<MS, NTV, 32, PR>(d, n_tiles, stream)
+  if (prec == 3) {
+    if (nt == 128) { if (msub == 2) DDG_LAUNCH(2, 128, 3); else DDG_LAUNCH(1, 128, 3); }
+    if (nt == 64) { if (msub == 2) DDG_LAUNCH(2, 64, 3); else DDG_LAUNCH(1, 64, 3); }
+    if (nt == 16) { if (msub == 2) DDG_LAUNCH(2, 16, 3); else DDG_LAUNCH(1, 16, 3); }
+  } else {
+    if (nt == 128) { if (msub == 2) DDG_LAUNCH(2, 128, 1); else DDG_LAUNCH(1, 128, 1); }
+    if (nt == 64) { if (msub == 2) DDG_LAUNCH(2, 64, 1); else DDG_LAUNCH(1, 64, 1); }
+    if (nt == 16) { if (msub == 2) DDG_LAUNCH(2, 16, 1); else DDG_LAUNCH(1, 16, 1); }
+  }
+#undef DDG_LAUNCH
+  ddg_set_last_error("conv2d_fwd: no kernel variant");
+  return DDG_ERR_UNSUPPORTED;
+}

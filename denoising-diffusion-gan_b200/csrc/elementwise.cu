@@ -1,0 +1,428 @@
+// Small fused kernels of the DDGAN hot path: embeddings, linear layers on [N, K] rows, the Gaussian updates of the
+// diffusion process, layout conversion and GroupNorm coefficient preparation.  All HBM-bound or latency-bound.
+#include "common.cuh"
+#include "ddgan_b200.h"
+
+namespace ddg {
+
+// layers.py:475-486
+__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* __restrict__ out, int N, int dim, float log_max) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * dim) return;
+  const int n = i / dim, j = i - n * dim;
+  float v = 0.f;
+  if (j < 2 * half) {
+    const int jj = j < half ? j : j - half;
+    // same operation order as the reference: exp(arange * -(log(max)/(half-1))), then t * freq
+    const float freq = expf((float)jj * -(log_max / (float)(half - 1)));
+    const float arg = (float)t[n] * freq;
+    v = j < half ? sinf(arg) : cosf(arg);
+  }
+  out[i] = v;
+}
+
+// y[n][j] = act_out(sum_k act_in(x[n][k]) W[j][k] + b[j]); one warp per output column, rows tiled by 32 in smem.
+constexpr int kLinRows = 32;
+__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                     const float* __restrict__ b, float* __restrict__ y, int N, int K, int J,
+                                                     int ldx, int ldy, int act_in, int act_out, int pixel_norm) {
+  extern __shared__ float sx[];  // [kLinRows][K]
+  const int n0 = blockIdx.y * kLinRows;
+  const int rows = min(kLinRows, N - n0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < rows; r += 8) {
+    const float* xr = x + (size_t)(n0 + r) * ldx;
+    float nrm = 1.f;
+    if (pixel_norm) {
+      float ss = 0.f;
+      for (int k = lane; k < K; k += 32) { const float v = xr[k]; ss += v * v; }
+      ss = warp_sum(ss);
+      nrm = 1.0f / sqrtf(ss / (float)K + 1e-8f);
+    }
+    for (int k = lane; k < K; k += 32) sx[r * K + k] = apply_act(xr[k] * nrm, act_in);
+  }
+  __syncthreads();
+  const int jpb = 8 * 4;  // 4 columns per warp per block
+  for (int jj = 0; jj < 4; ++jj) {
+    const int j = blockIdx.x * jpb + warp * 4 + jj;
+    if (j >= J) break;
+    const float* wr = W + (size_t)j * K;
+    const float bj = b ? b[j] : 0.f;
+    for (int r = 0; r < rows; ++r) {
+      float acc = 0.f;
+      for (int k = lane; k < K; k += 32) acc = fmaf(sx[r * K + k], __ldg(wr + k), acc);
+      acc = warp_sum(acc);
+      if (lane == 0) y[(size_t)(n0 + r) * ldy + j] = apply_act(acc + bj, act_out);
+    }
+  }
+}
+
+// ddgan.py:110-126
+__global__ void q_sample_pairs_kernel(const float4* __restrict__ x0, const float4* __restrict__ n0, const float4* __restrict__ n1,
+                                      const int64_t* __restrict__ t, const float* __restrict__ a_cum, const float* __restrict__ s_cum,
+                                      const float* __restrict__ a_s, const float* __restrict__ sig, float4* __restrict__ xt,
+                                      float4* __restrict__ xtp1, long per4, long total4) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / per4);
+    const int tt = (int)t[n];
+    const float ac = a_cum[tt], sc = s_cum[tt], a1 = a_s[tt + 1], s1 = sig[tt + 1];
+    const float4 x = ldg_stream(x0 + i), e0 = ldg_stream(n0 + i), e1 = ldg_stream(n1 + i);
+    float4 a, b;
+    a.x = ac * x.x + sc * e0.x; a.y = ac * x.y + sc * e0.y; a.z = ac * x.z + sc * e0.z; a.w = ac * x.w + sc * e0.w;
+    b.x = a1 * a.x + s1 * e1.x; b.y = a1 * a.y + s1 * e1.y; b.z = a1 * a.z + s1 * e1.z; b.w = a1 * a.w + s1 * e1.w;
+    stg_stream(xt + i, a);
+    stg_stream(xtp1 + i, b);
+  }
+}
+
+// ddgan.py:152-169: mean = c1[t] x0 + c2[t] x_t ; out = mean + (t != 0) * exp(0.5 logvar[t]) * noise
+__global__ void sample_posterior_kernel(const float4* __restrict__ x0, const float4* __restrict__ xt, const float4* __restrict__ nz,
+                                        const int64_t* __restrict__ t, const float* __restrict__ c1, const float* __restrict__ c2,
+                                        const float* __restrict__ logvar, float4* __restrict__ out, long per4, long total4) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / per4);
+    const int tt = (int)t[n];
+    const float k1 = c1[tt], k2 = c2[tt];
+    const float sd = (tt != 0 ? 1.f : 0.f) * expf(0.5f * logvar[tt]);
+    const float4 a = ldg_stream(x0 + i), b = ldg_stream(xt + i), e = ldg_stream(nz + i);
+    float4 o;
+    o.x = (k1 * a.x + k2 * b.x) + sd * e.x;
+    o.y = (k1 * a.y + k2 * b.y) + sd * e.y;
+    o.z = (k1 * a.z + k2 * b.z) + sd * e.z;
+    o.w = (k1 * a.w + k2 * b.w) + sd * e.w;
+    stg_stream(out + i, o);
+  }
+}
+
+// scalar-tail variants (per_sample not a multiple of 4)
+__global__ void q_sample_pairs_scalar(const float* x0, const float* n0, const float* n1, const int64_t* t, const float* a_cum,
+                                      const float* s_cum, const float* a_s, const float* sig, float* xt, float* xtp1, long per,
+                                      long total) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int tt = (int)t[i / per];
+    const float a = a_cum[tt] * x0[i] + s_cum[tt] * n0[i];
+    xt[i] = a;
+    xtp1[i] = a_s[tt + 1] * a + sig[tt + 1] * n1[i];
+  }
+}
+__global__ void sample_posterior_scalar(const float* x0, const float* xt, const float* nz, const int64_t* t, const float* c1,
+                                        const float* c2, const float* logvar, float* out, long per, long total) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int tt = (int)t[i / per];
+    const float sd = (tt != 0 ? 1.f : 0.f) * expf(0.5f * logvar[tt]);
+    out[i] = (c1[tt] * x0[i] + c2[tt] * xt[i]) + sd * nz[i];
+  }
+}
+
+// NCHW (a ++ b along C) -> PNHWC interior, channels >= Ca+Cb zero.  One thread per (n, h, w); writes Cpad floats.
+__global__ void nchw_to_pnhwc_kernel(const float* __restrict__ a, int Ca, const float* __restrict__ b, int Cb, float* __restrict__ out,
+                                     int N, int H, int W, int Cpad, float scale, float shift) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long total = (long)N * H * W * (Cpad / 4);
+  if (i >= total) return;
+  const int c4 = (int)(i % (Cpad / 4));
+  long r = i / (Cpad / 4);
+  const int w = (int)(r % W); r /= W;
+  const int h = (int)(r % H);
+  const int n = (int)(r / H);
+  float v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c4 * 4 + j;
+    float x = 0.f;
+    if (c < Ca) x = a[((size_t)(n * Ca + c) * H + h) * W + w] * scale + shift;
+    else if (c < Ca + Cb) x = b[((size_t)(n * Cb + (c - Ca)) * H + h) * W + w] * scale + shift;
+    v[j] = x;
+  }
+  float4* o = reinterpret_cast<float4*>(out + ((size_t)(n * (H + 2) + h + 1) * (W + 2) + (w + 1)) * Cpad) + c4;
+  *o = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// PNHWC / NHWC -> NCHW through a 32x32 smem transpose (coalesced on both sides)
+__global__ void pnhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int H, int W, int C, int Cpitch,
+                                     int padded) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int HW = H * W;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int p = p0 + r, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (p < HW && c < C) {
+      const int h = p / W, w = p - h * W;
+      const size_t pix = padded ? ((size_t)(n * (H + 2) + h + 1) * (W + 2) + (w + 1)) : ((size_t)n * HW + p);
+      v = x[pix * Cpitch + c];
+    }
+    tile[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r, p = p0 + threadIdx.x;
+    if (p < HW && c < C) out[((size_t)n * C + c) * HW + p] = tile[threadIdx.x][r];
+  }
+}
+
+// GroupNorm coefficients from per-(n,c) {sum, sumsq}: one block per sample, one thread per channel.
+__global__ void gn_prepare_kernel(const double* __restrict__ sa, int Ca, const double* __restrict__ sb, int Cb,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, int gb_stride, int per_sample,
+                                  float* __restrict__ scale, float* __restrict__ shift, int HW, int G, float eps) {
+  extern __shared__ double sred[];  // [2*C]
+  const int n = blockIdx.x;
+  const int C = Ca + Cb;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double* s = c < Ca ? sa + ((size_t)n * Ca + c) * 2 : sb + ((size_t)n * Cb + (c - Ca)) * 2;
+    sred[2 * c] = s[0];
+    sred[2 * c + 1] = s[1];
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    double s1 = 0, s2 = 0;
+    for (int j = 0; j < cpg; ++j) { s1 += sred[2 * (g * cpg + j)]; s2 += sred[2 * (g * cpg + j) + 1]; }
+    const double cnt = (double)cpg * HW;
+    const double mean = s1 / cnt;
+    double var = s2 / cnt - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    float ga = 1.f, be = 0.f;
+    if (gamma) {
+      ga = per_sample ? gamma[(size_t)n * gb_stride + c] : gamma[c];
+      be = per_sample ? beta[(size_t)n * gb_stride + c] : beta[c];
+    }
+    const float sc = ga * rstd;
+    scale[(size_t)n * C + c] = sc;
+    shift[(size_t)n * C + c] = be - (float)mean * sc;
+  }
+}
+
+// out[n][c] = sum over interior pixels of act(x)
+__global__ void spatial_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int H, int W, int C, int act) {
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int h = 0; h < H; ++h)
+    for (int w = 0; w < W; ++w) acc += apply_act(x[((size_t)(n * (H + 2) + h + 1) * (W + 2) + (w + 1)) * C + c], act);
+  out[(size_t)n * C + c] = acc;
+}
+
+// discriminator.py:150-158.  group = min(N, 4); M = N / group; sample i belongs to stat-set (i % M);
+// std over the `group` members, mean over (C, H, W) -> one scalar per stat-set, broadcast to channel 0 of out.
+__global__ void minibatch_stddev_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int H, int W, int C, int Cpad,
+                                        int group) {
+  const int M = N / group;
+  const int m = blockIdx.x;
+  const long per = (long)H * W * C;
+  double acc = 0.0;
+  for (long i = threadIdx.x; i < per; i += blockDim.x) {
+    const int c = (int)(i % C);
+    long r = i / C;
+    const int w = (int)(r % W);
+    const int h = (int)(r / W);
+    float vals[4];
+    float mean = 0.f;
+    for (int g = 0; g < group; ++g) {
+      const int n = g * M + m;
+      vals[g] = x[((size_t)(n * (H + 2) + h + 1) * (W + 2) + (w + 1)) * C + c];
+      mean += vals[g];
+    }
+    mean /= (float)group;
+    float var = 0.f;
+    for (int g = 0; g < group; ++g) { const float d = vals[g] - mean; var += d * d; }
+    var /= (float)group;
+    acc += (double)sqrtf(var + 1e-8f);
+  }
+  __shared__ double red[32];
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    v = warp_sum_d(v);
+    if (threadIdx.x == 0) red[0] = v / (double)per;
+  }
+  __syncthreads();
+  const float s = (float)red[0];
+  for (int i = threadIdx.x; i < group * H * W; i += blockDim.x) {
+    const int g = i / (H * W);
+    const int r = i - g * H * W;
+    const int h = r / W, w = r - h * W;
+    const int n = g * M + m;
+    float* o = out + ((size_t)(n * (H + 2) + h + 1) * (W + 2) + (w + 1)) * Cpad;
+    o[0] = s;
+  }
+}
+
+// grad_bias reduction: out[c] = sum_{n, inner} g[n][c][inner]
+__global__ void channel_sum_kernel(const float* __restrict__ g, float* __restrict__ out, int N, int C, int inner) {
+  const int c = blockIdx.x;
+  double acc = 0.0;
+  for (int n = 0; n < N; ++n) {
+    const float* p = g + ((size_t)n * C + c) * inner;
+    for (int i = threadIdx.x; i < inner; i += blockDim.x) acc += (double)p[i];
+  }
+  __shared__ double red[32];
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    v = warp_sum_d(v);
+    if (threadIdx.x == 0) out[c] = (float)v;
+  }
+}
+
+}  // namespace ddg
+
+using namespace ddg;
+
+static inline int grid_for(long total, int threads, int cap = 148 * 32) {
+  long b = (total + threads - 1) / threads;
+  if (b < 1) b = 1;
+  return (int)(b > cap ? cap : b);
+}
+
+extern "C" int ddg_timestep_embedding(const int64_t* t, float* out, int N, int dim, float max_positions, cudaStream_t stream) {
+  if (!t || !out || N <= 0 || dim < 4) { ddg_set_last_error("timestep_embedding: bad args"); return DDG_ERR_ARG; }
+  const int total = N * dim;
+  timestep_embedding_kernel<<<(total + 255) / 256, 256, 0, stream>>>(t, out, N, dim, logf(max_positions));
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}
+
+extern "C" int ddg_linear(const float* x, const float* W, const float* b, float* y, int N, int K, int J, int ldx, int ldy,
+                          int act_in, int act_out, int pixel_norm, cudaStream_t stream) {
+  if (!x || !W || !y || N <= 0 || K <= 0 || J <= 0) { ddg_set_last_error("linear: bad args"); return DDG_ERR_ARG; }
+  const size_t smem = (size_t)kLinRows * K * sizeof(float);
+  if (smem > 200 * 1024) { ddg_set_last_error("linear: K too large"); return DDG_ERR_UNSUPPORTED; }
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  dim3 grid((J + 31) / 32, (N + kLinRows - 1) / kLinRows);
+  linear_kernel<<<grid, 256, smem, stream>>>(x, W, b, y, N, K, J, ldx, ldy, act_in, act_out, pixel_norm);
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}
+
+extern "C" int ddg_q_sample_pairs(const float* x0, const float* noise_xt, const float* noise_xtp1, const int64_t* t,
+                                  const float* a_s_cum, const float* sigmas_cum, const float* a_s, const float* sigmas, float* x_t,
+                                  float* x_tp1, int N, long per_sample, cudaStream_t stream) {
+  if (!x0 || !noise_xt || !noise_xtp1 || !t || !x_t || !x_tp1 || N <= 0 || per_sample <= 0) { ddg_set_last_error("q_sample_pairs: bad args"); return DDG_ERR_ARG; }
+  const long total = (long)N * per_sample;
+  const bool vec = (per_sample % 4 == 0) && ((((uintptr_t)x0 | (uintptr_t)noise_xt | (uintptr_t)noise_xtp1 | (uintptr_t)x_t | (uintptr_t)x_tp1) & 15) == 0);
+  if (vec)
+    q_sample_pairs_kernel<<<grid_for(total / 4, 256), 256, 0, stream>>>((const float4*)x0, (const float4*)noise_xt, (const float4*)noise_xtp1, t, a_s_cum,
+                                                                       sigmas_cum, a_s, sigmas, (float4*)x_t, (float4*)x_tp1, per_sample / 4, total / 4);
+  else
+    q_sample_pairs_scalar<<<grid_for(total, 256), 256, 0, stream>>>(x0, noise_xt, noise_xtp1, t, a_s_cum, sigmas_cum, a_s, sigmas, x_t, x_tp1, per_sample, total);
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}
+
+extern "C" int ddg_sample_posterior(const float* x0, const float* x_t, const float* noise, const int64_t* t, const float* coef1,
+                                    const float* coef2, const float* logvar, float* out, int N, long per_sample, cudaStream_t stream) {
+  if (!x0 || !x_t || !noise || !t || !out || N <= 0 || per_sample <= 0) { ddg_set_last_error("sample_posterior: bad args"); return DDG_ERR_ARG; }
+  const long total = (long)N * per_sample;
+  const bool vec = (per_sample % 4 == 0) && ((((uintptr_t)x0 | (uintptr_t)x_t | (uintptr_t)noise | (uintptr_t)out) & 15) == 0);
+  if (vec)
+    sample_posterior_kernel<<<grid_for(total / 4, 256), 256, 0, stream>>>((const float4*)x0, (const float4*)x_t, (const float4*)noise, t, coef1, coef2,
+                                                                         logvar, (float4*)out, per_sample / 4, total / 4);
+  else
+    sample_posterior_scalar<<<grid_for(total, 256), 256, 0, stream>>>(x0, x_t, noise, t, coef1, coef2, logvar, out, per_sample, total);
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}
+
+extern "C" int ddg_nchw_to_pnhwc(const float* a, int Ca, const float* b, int Cb, float* out, int N, int H, int W, int Cpad, float scale,
+                                 float shift, cudaStream_t stream) {
+  if (!a || !out || Cpad % 4 != 0 || Ca + Cb > Cpad) { ddg_set_last_error("nchw_to_pnhwc: bad args"); return DDG_ERR_ARG; }
+  const long total = (long)N * H * W * (Cpad / 4);
+  nchw_to_pnhwc_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(a, Ca, b, b ? Cb : 0, out, N, H, W, Cpad, scale, shift);
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}
+
+extern "C" int ddg_pnhwc_to_nchw(const float* x, float* out, int N, int H, int W, int C, int Cpitch, int padded, cudaStream_t stream) {
+  if (!x || !out) { ddg_set_last_error("pnhwc_to_nchw: bad args"); return DDG_ERR_ARG; }
+  dim3 grid((H * W + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  pnhwc_to_nchw_kernel<<<grid, block, 0, stream>>>(x, out, N, H, W, C, Cpitch, padded);
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}
+
+extern "C" int ddg_gn_prepare(const double* stats_a, int Ca, const double* stats_b, int Cb, const float* gamma, const float* beta,
+                              int gb_stride, int per_sample, float* scale, float* shift, int N, int HW, int G, float eps,
+                              cudaStream_t stream) {
+  const int C = Ca + (stats_b ? Cb : 0);
+  if (!stats_a || !scale || !shift || G <= 0 || C % G != 0) { ddg_set_last_error("gn_prepare: bad args"); return DDG_ERR_ARG; }
+  gn_prepare_kernel<<<N, 256, 2 * C * sizeof(double), stream>>>(stats_a, Ca, stats_b, stats_b ? Cb : 0, gamma, beta, gb_stride, per_sample,
+                                                                scale, shift, HW, G, eps);
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}
+
+extern "C" int ddg_spatial_sum(const float* x, float* out, int N, int H, int W, int C, int act, cudaStream_t stream) {
+  if (!x || !out) { ddg_set_last_error("spatial_sum: bad args"); return DDG_ERR_ARG; }
+  dim3 grid((C + 127) / 128, N);
+  spatial_sum_kernel<<<grid, 128, 0, stream>>>(x, out, H, W, C, act);
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}
+
+extern "C" int ddg_minibatch_stddev(const float* x, float* out, int N, int H, int W, int C, int Cpad, int group, cudaStream_t stream) {
+  if (!x || !out || group < 1 || group > 4 || N % group != 0) { ddg_set_last_error("minibatch_stddev: bad args"); return DDG_ERR_ARG; }
+  minibatch_stddev_kernel<<<N / group, 256, 0, stream>>>(x, out, N, H, W, C, Cpad, group);
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}
+
+extern "C" int ddg_channel_sum(const float* g, float* out, int N, int C, int inner, cudaStream_t stream) {
+  if (!g || !out) { ddg_set_last_error("channel_sum: bad args"); return DDG_ERR_ARG; }
+  channel_sum_kernel<<<C, 256, 0, stream>>>(g, out, N, C, inner);
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}
+
+namespace ddg {
+// one warp per row, T <= 32*32
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, float* __restrict__ p, long rows, int T, int lds,
+                                                          int ldp) {
+  const long row = blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* sr = s + row * lds;
+  float* pr = p + row * ldp;
+  float v[32];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int j = lane + 32 * i;
+    v[i] = j < T ? sr[j] : -INFINITY;
+    mx = fmaxf(mx, v[i]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int j = lane + 32 * i;
+    v[i] = j < T ? expf(v[i] - mx) : 0.f;
+    sum += v[i];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int j = lane + 32 * i;
+    if (j < ldp) pr[j] = j < T ? v[i] * inv : 0.f;
+  }
+}
+}  // namespace ddg
+
+extern "C" int ddg_softmax_rows(const float* s, float* p, long rows, int T, int lds, int ldp, cudaStream_t stream) {
+  if (!s || !p || T <= 0 || T > 1024 || ldp > 1024 || lds < T || ldp < T) { ddg_set_last_error("softmax_rows: bad args (T <= 1024)"); return DDG_ERR_ARG; }
+  ddg::softmax_rows_kernel<<<(int)((rows + 7) / 8), 256, 0, stream>>>(s, p, rows, T, lds, ldp);
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}

@@ -1,0 +1,199 @@
+// upfirdn2d for sm_100a: pad -> zero-insert up -> FIR (true convolution) -> decimate.
+// Replaces score_sde/op/upfirdn2d_kernel.cu:51-371 behind the same argument list (upfirdn2d.cpp:20-31).
+//
+// The reference launches one 256-thread CTA per 16x64 / 8x32 output tile per (N*C) plane, which is 6-50 % filled on
+// the <= 32 px maps of the CIFAR config.  Here a plane is a contiguous run of memory, the
+// grid is a flat grid-stride loop over float4 groups of outputs (HBM-bound op: bytes = 4*(in + out) per plane) and
+// only the polyphase taps that hit a non-zero sample are visited (4 of 16 for up=2).
+#include "common.cuh"
+#include "ddgan_b200.h"
+
+namespace ddg {
+
+constexpr int kMaxTaps = 256;
+
+struct UpfirdnParams {
+  int in_h, in_w, out_h, out_w, kh, kw;
+  int up_x, up_y, down_x, down_y, pad_x0, pad_y0;
+};
+
+// generic: VEC consecutive outputs along x per thread
+template <int VEC>
+__global__ void __launch_bounds__(256) upfirdn2d_kernel(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ out,
+                                                        long planes, UpfirdnParams p) {
+  __shared__ float sk[kMaxTaps];  // flipped kernel: sk[i][j] = k[kh-1-i][kw-1-j]
+  for (int i = threadIdx.x; i < p.kh * p.kw; i += blockDim.x) {
+    const int r = i / p.kw, c = i - r * p.kw;
+    sk[i] = k[(p.kh - 1 - r) * p.kw + (p.kw - 1 - c)];
+  }
+  __syncthreads();
+  const int wv = (p.out_w + VEC - 1) / VEC;
+  const long total = planes * p.out_h * wv;
+  const long in_plane = (long)p.in_h * p.in_w, out_plane = (long)p.out_h * p.out_w;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int xv = (int)(idx % wv);
+    long r = idx / wv;
+    const int oy = (int)(r % p.out_h);
+    const long pl = r / p.out_h;
+    const float* xin = x + pl * in_plane;
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    const int base_y = oy * p.down_y - p.pad_y0;
+    int i0 = (-base_y) % p.up_y;
+    if (i0 < 0) i0 += p.up_y;
+    for (int i = i0; i < p.kh; i += p.up_y) {
+      const int a = base_y + i;
+      if (a < 0) continue;
+      const int iy = a / p.up_y;
+      if (iy >= p.in_h) break;
+      const float* row = xin + (long)iy * p.in_w;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const int ox = xv * VEC + v;
+        const int base_x = ox * p.down_x - p.pad_x0;
+        int j0 = (-base_x) % p.up_x;
+        if (j0 < 0) j0 += p.up_x;
+        for (int j = j0; j < p.kw; j += p.up_x) {
+          const int b = base_x + j;
+          if (b < 0) continue;
+          const int ix = b / p.up_x;
+          if (ix >= p.in_w) break;
+          acc[v] = fmaf(__ldg(row + ix), sk[i * p.kw + j], acc[v]);
+        }
+      }
+    }
+    float* o = out + pl * out_plane + (long)oy * p.out_w + xv * VEC;
+    if (VEC == 4 && xv * 4 + 3 < p.out_w && ((((uintptr_t)o) & 15) == 0)) {
+      stg_stream(reinterpret_cast<float4*>(o), make_float4(acc[0], acc[1], acc[2], acc[3]));
+    } else {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v)
+        if (xv * VEC + v < p.out_w) o[v] = acc[v];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// FIR on the internal PNHWC layout, [1,3,3,1] (x) [1,3,3,1] / 64 (up: x4 gain), AdaGN + activation fused on load.
+// One thread per (output pixel, 4 channels).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 load_tr(const float* __restrict__ x, size_t off, const float4& sc, const float4& sh, bool affine,
+                                          int act) {
+  float4 v = __ldg(reinterpret_cast<const float4*>(x + off));
+  if (affine) { v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w); }
+  if (act != ACT_NONE) { v.x = apply_act(v.x, act); v.y = apply_act(v.y, act); v.z = apply_act(v.z, act); v.w = apply_act(v.w, act); }
+  return v;
+}
+__device__ __forceinline__ void fma4(float4& a, const float4& v, float w) {
+  a.x = fmaf(v.x, w, a.x); a.y = fmaf(v.y, w, a.y); a.z = fmaf(v.z, w, a.z); a.w = fmaf(v.w, w, a.w);
+}
+
+// mode 1: up2 (H -> 2H), mode 2: down2 (H -> H/2), mode 3: pad(2,2) FIR H -> H+1 stored space-to-depth
+__global__ void __launch_bounds__(256) fir_pnhwc_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                                        const float* __restrict__ shift, int act, float* __restrict__ out, int N, int H,
+                                                        int W, int C, int mode, int out_pitch) {
+  const float t4[4] = {1.f, 3.f, 3.f, 1.f};
+  const int C4 = C / 4;
+  int OH, OW;
+  if (mode == 1) { OH = 2 * H; OW = 2 * W; } else if (mode == 2) { OH = H / 2; OW = W / 2; } else { OH = H + 1; OW = W + 1; }
+  const long total = (long)N * OH * OW * C4;
+  const bool affine = scale != nullptr;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(idx % C4);
+    long r = idx / C4;
+    const int ox = (int)(r % OW); r /= OW;
+    const int oy = (int)(r % OH);
+    const int n = (int)(r / OH);
+    float4 sc = make_float4(1, 1, 1, 1), sh = make_float4(0, 0, 0, 0);
+    if (affine) {
+      sc = __ldg(reinterpret_cast<const float4*>(scale + (size_t)n * C) + c4);
+      sh = __ldg(reinterpret_cast<const float4*>(shift + (size_t)n * C) + c4);
+    }
+    float4 acc = make_float4(0, 0, 0, 0);
+    // In every mode out[oy][ox] = sum_{i,j} in[(oy*down + i - pad)/up] * kflip[i][j] over contributing taps; the
+    // separable [1,3,3,1] kernel is symmetric so kflip == k.
+    if (mode == 1) {
+      // up=2, pad0=2: a = oy + i - 2 must be even and in range; weights k*4/64
+      for (int i = (oy & 1); i < 4; i += 2) {
+        const int iy = (oy + i - 2) >> 1;
+        if (oy + i - 2 < 0 || iy >= H) continue;
+        for (int j = (ox & 1); j < 4; j += 2) {
+          const int ix = (ox + j - 2) >> 1;
+          if (ox + j - 2 < 0 || ix >= W) continue;
+          const size_t off = ((size_t)(n * (H + 2) + iy + 1) * (W + 2) + (ix + 1)) * C + c4 * 4;
+          fma4(acc, load_tr(x, off, sc, sh, affine, act), t4[i] * t4[j] * (4.f / 64.f));
+        }
+      }
+    } else {
+      const int down = (mode == 2) ? 2 : 1;
+      const int pad = (mode == 2) ? 1 : 2;
+      for (int i = 0; i < 4; ++i) {
+        const int iy = oy * down + i - pad;
+        if (iy < 0 || iy >= H) continue;
+        for (int j = 0; j < 4; ++j) {
+          const int ix = ox * down + j - pad;
+          if (ix < 0 || ix >= W) continue;
+          const size_t off = ((size_t)(n * (H + 2) + iy + 1) * (W + 2) + (ix + 1)) * C + c4 * 4;
+          fma4(acc, load_tr(x, off, sc, sh, affine, act), t4[i] * t4[j] * (1.f / 64.f));
+        }
+      }
+    }
+    size_t ooff;
+    if (mode == 3) {
+      // space-to-depth cell (oy/2, ox/2), sub-position (oy&1, ox&1); buffer [N][Ho+3][Wo+3][out_pitch], Ho = H/2
+      const int Hc = H / 2 + 3, Wc = W / 2 + 3;
+      ooff = ((size_t)(n * Hc + (oy >> 1) + 1) * Wc + ((ox >> 1) + 1)) * out_pitch + (size_t)((oy & 1) * 2 + (ox & 1)) * C + c4 * 4;
+    } else {
+      ooff = ((size_t)(n * (OH + 2) + oy + 1) * (OW + 2) + (ox + 1)) * out_pitch + c4 * 4;
+    }
+    *reinterpret_cast<float4*>(out + ooff) = acc;
+  }
+}
+
+}  // namespace ddg
+
+using namespace ddg;
+
+extern "C" int ddg_upfirdn2d_out_size(int in_size, int up, int down, int pad0, int pad1, int ksize) {
+  return (in_size * up + pad0 + pad1 - ksize) / down + 1;
+}
+
+extern "C" int ddg_upfirdn2d(const float* x, const float* k, float* out, long planes, int in_h, int in_w, int kh, int kw, int up_x,
+                             int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1, cudaStream_t stream) {
+  if (!x || !k || !out || planes < 0 || in_h <= 0 || in_w <= 0 || kh <= 0 || kw <= 0 || up_x < 1 || up_y < 1 || down_x < 1 || down_y < 1) {
+    ddg_set_last_error("upfirdn2d: bad args");
+    return DDG_ERR_ARG;
+  }
+  if (kh * kw > kMaxTaps) { ddg_set_last_error("upfirdn2d: kernel larger than 256 taps"); return DDG_ERR_UNSUPPORTED; }
+  UpfirdnParams p;
+  p.in_h = in_h; p.in_w = in_w; p.kh = kh; p.kw = kw;
+  p.up_x = up_x; p.up_y = up_y; p.down_x = down_x; p.down_y = down_y; p.pad_x0 = pad_x0; p.pad_y0 = pad_y0;
+  p.out_h = (in_h * up_y + pad_y0 + pad_y1 - kh) / down_y + 1;
+  p.out_w = (in_w * up_x + pad_x0 + pad_x1 - kw) / down_x + 1;
+  if (p.out_h <= 0 || p.out_w <= 0) { ddg_set_last_error("upfirdn2d: empty output"); return DDG_ERR_ARG; }
+  if (planes == 0) return DDG_OK;
+  const bool vec = (p.out_w % 4 == 0);
+  const long total = planes * p.out_h * (vec ? p.out_w / 4 : p.out_w);
+  long blocks = (total + 255) / 256;
+  if (blocks > 148L * 64) blocks = 148L * 64;
+  if (vec) upfirdn2d_kernel<4><<<(int)blocks, 256, 0, stream>>>(x, k, out, planes, p);
+  else upfirdn2d_kernel<1><<<(int)blocks, 256, 0, stream>>>(x, k, out, planes, p);
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}
+
+extern "C" int ddg_fir_pnhwc(const float* x, const float* scale, const float* shift, int act, float* out, int N, int H, int W, int C,
+                             int mode, int out_pitch, double* stats, cudaStream_t stream) {
+  (void)stats;
+  if (!x || !out || C % 4 != 0 || mode < 1 || mode > 3 || ((scale == nullptr) != (shift == nullptr))) { ddg_set_last_error("fir_pnhwc: bad args"); return DDG_ERR_ARG; }
+  if ((mode == 2 || mode == 3) && ((H | W) & 1)) { ddg_set_last_error("fir_pnhwc: odd size"); return DDG_ERR_UNSUPPORTED; }
+  int OH = mode == 1 ? 2 * H : (mode == 2 ? H / 2 : H + 1);
+  int OW = mode == 1 ? 2 * W : (mode == 2 ? W / 2 : W + 1);
+  const long total = (long)N * OH * OW * (C / 4);
+  long blocks = (total + 255) / 256;
+  if (blocks > 148L * 32) blocks = 148L * 32;
+  fir_pnhwc_kernel<<<(int)blocks, 256, 0, stream>>>(x, scale, shift, act, out, N, H, W, C, mode, out_pitch);
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}

@@ -1,0 +1,105 @@
+"""ctypes binding of libddgan_b200.so (the C ABI declared in include/ddgan_b200.h).
+
+There is no CPU fallback: if the library is missing, importing any op raises.  PyTorch is used only for device
+memory, streams and autograd plumbing; every call below passes raw device pointers and the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libddgan_b200.so')
+
+MAX_SRC = 3
+
+
+class ConvSrc(C.Structure):
+    _fields_ = [('x', C.c_void_p), ('scale', C.c_void_p), ('shift', C.c_void_p), ('C', C.c_int), ('act', C.c_int),
+                ('ntaps', C.c_int), ('padded', C.c_int), ('tap_dr', C.c_int8 * 9), ('tap_ds', C.c_int8 * 9)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [('src', ConvSrc * MAX_SRC), ('nsrc', C.c_int), ('wpack', C.c_void_p), ('kb', C.c_int), ('N', C.c_int),
+                ('Hout', C.c_int), ('Wout', C.c_int), ('Hp', C.c_int), ('Wp', C.c_int), ('Cout', C.c_int),
+                ('bias', C.c_void_p), ('addvec', C.c_void_p), ('addvec_stride', C.c_int), ('res', C.c_void_p),
+                ('out_scale', C.c_float), ('out_act', C.c_int), ('out', C.c_void_p), ('out_mode', C.c_int),
+                ('out_C', C.c_int), ('stats', C.c_void_p), ('precision', C.c_int), ('msub', C.c_int),
+                ('batch_rows', C.c_int), ('debug_swap_lbo_sbo', C.c_int)]
+
+
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_long, C.c_float
+
+_SIGNATURES = {
+    'ddg_version': ([], _I),
+    'ddg_upfirdn2d': ([_P, _P, _P, _L] + [_I] * 12 + [_P], _I),
+    'ddg_upfirdn2d_out_size': ([_I] * 6, _I),
+    'ddg_fused_bias_act': ([_P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _P], _I),
+    'ddg_channel_sum': ([_P, _P, _I, _I, _I, _P], _I),
+    'ddg_groupnorm_fwd': ([_P] * 6 + [_I] * 4 + [_F, _I, _I, _P], _I),
+    'ddg_groupnorm_bwd': ([_P] * 9 + [_I] * 6 + [_P], _I),
+    'ddg_timestep_embedding': ([_P, _P, _I, _I, _F, _P], _I),
+    'ddg_linear': ([_P] * 4 + [_I] * 8 + [_P], _I),
+    'ddg_q_sample_pairs': ([_P] * 10 + [_I, _L, _P], _I),
+    'ddg_sample_posterior': ([_P] * 8 + [_I, _L, _P], _I),
+    'ddg_nchw_to_pnhwc': ([_P, _I, _P, _I, _P, _I, _I, _I, _I, _F, _F, _P], _I),
+    'ddg_pnhwc_to_nchw': ([_P, _P] + [_I] * 6 + [_P], _I),
+    'ddg_gn_prepare': ([_P, _I, _P, _I, _P, _P, _I, _I, _P, _P, _I, _I, _I, _F, _P], _I),
+    'ddg_fir_pnhwc': ([_P, _P, _P, _I, _P] + [_I] * 6 + [_P, _P], _I),
+    'ddg_minibatch_stddev': ([_P, _P] + [_I] * 6 + [_P], _I),
+    'ddg_spatial_sum': ([_P, _P] + [_I] * 5 + [_P], _I),
+    'ddg_softmax_rows': ([_P, _P, _L, _I, _I, _I, _P], _I),
+    'ddg_conv_tile_n': ([_I], _I),
+    'ddg_conv_packed_bytes': ([_I, _I, _I, _I], _L),
+    'ddg_conv_pack_weights': ([_P, _P, _I, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _I, _I, _L, _P], _I),
+    'ddg_conv2d_fwd': ([C.POINTER(ConvDesc), _P], _I),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f'{LIB_PATH} is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+                               '(or denoising-diffusion-gan_b200/csrc/build.sh). There is no CPU fallback.')
+        l = C.CDLL(LIB_PATH)
+        l.ddg_last_error.restype = C.c_char_p
+        l.ddg_last_error.argtypes = []
+        for name, (args, res) in _SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = args
+            fn.restype = res
+        _lib = l
+    return _lib
+
+
+def exported_symbols():
+    return ['ddg_last_error'] + list(_SIGNATURES)
+
+
+def check(rc: int, what: str = ''):
+    if rc != 0:
+        raise RuntimeError(f'libddgan_b200 {what} failed ({rc}): {lib().ddg_last_error().decode()}')
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda_f32(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError('ddgan_b200 ops run on CUDA tensors only (no CPU fallback)')
+        if t.dtype != torch.float32:
+            raise RuntimeError(f'ddgan_b200 ops are fp32 at the boundary, got {t.dtype}')

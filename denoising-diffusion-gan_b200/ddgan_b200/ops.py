@@ -1,0 +1,303 @@
+"""Thin, allocation-explicit Python wrappers over the C ABI (one function per entry point).
+
+Nothing here computes on the host or falls back to torch ops: each wrapper validates, allocates the output with
+torch (device memory plumbing only) and calls libddgan_b200.so on the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, check, lib, ptr, require_cuda_f32, stream
+
+ACT_NONE, ACT_SILU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3
+OUT_PNHWC, OUT_NHWC, OUT_NCHW = 0, 1, 2
+KB = 32
+
+TAPS_3X3 = [(r - 1, s - 1) for r in range(3) for s in range(3)]
+TAPS_2X2 = [(dy, dx) for dy in range(2) for dx in range(2)]
+TAPS_1X1 = [(0, 0)]
+
+
+def pad_c(c: int, m: int = KB) -> int:
+    return (c + m - 1) // m * m
+
+
+# ---------------------------------------------------------------------------------------------------------
+# score_sde.op surface primitives
+# ---------------------------------------------------------------------------------------------------------
+def upfirdn2d_raw(x: torch.Tensor, k: torch.Tensor, up_x, up_y, down_x, down_y, px0, px1, py0, py1) -> torch.Tensor:
+    """x [planes, H, W] -> [planes, H', W'] (upfirdn2d.cpp:20-31 argument order)."""
+    require_cuda_f32(x, k)
+    x = x.contiguous()
+    k = k.contiguous()
+    planes, in_h, in_w = x.shape
+    kh, kw = k.shape
+    out_h = (in_h * up_y + py0 + py1 - kh) // down_y + 1
+    out_w = (in_w * up_x + px0 + px1 - kw) // down_x + 1
+    out = torch.empty(planes, out_h, out_w, device=x.device, dtype=torch.float32)
+    check(lib().ddg_upfirdn2d(ptr(x), ptr(k), ptr(out), planes, in_h, in_w, kh, kw, up_x, up_y, down_x, down_y,
+                              px0, px1, py0, py1, stream()), 'upfirdn2d')
+    return out
+
+
+def fused_bias_act(x, b, ref, act: int, grad: int, alpha: float, scale: float) -> torch.Tensor:
+    """fused_bias_act.cpp:18-28; b / ref may be None or 0-element ('absent')."""
+    require_cuda_f32(x)
+    x = x.contiguous()
+    b = None if (b is None or b.numel() == 0) else b.contiguous()
+    ref = None if (ref is None or ref.numel() == 0) else ref.contiguous()
+    y = torch.empty_like(x)
+    step_b = 1
+    for d in x.shape[2:]:
+        step_b *= d
+    size_b = b.numel() if b is not None else 1
+    check(lib().ddg_fused_bias_act(ptr(x), ptr(b), ptr(ref), ptr(y), x.numel(), step_b, size_b, act, grad, alpha, scale,
+                                   stream()), 'fused_bias_act')
+    return y
+
+
+def channel_sum(g: torch.Tensor) -> torch.Tensor:
+    """[N, C, ...] -> [C]"""
+    require_cuda_f32(g)
+    g = g.contiguous()
+    n, c = g.shape[0], g.shape[1]
+    inner = g.numel() // max(n * c, 1)
+    out = torch.empty(c, device=g.device, dtype=torch.float32)
+    check(lib().ddg_channel_sum(ptr(g), ptr(out), n, c, inner, stream()), 'channel_sum')
+    return out
+
+
+def groupnorm_fwd(x, G, gamma=None, beta=None, eps=1e-6, per_sample=False, act=ACT_NONE):
+    """NCHW GroupNorm(+AdaGN affine, + activation). Returns (y, mean[N*G], rstd[N*G])."""
+    require_cuda_f32(x, gamma, beta)
+    x = x.contiguous()
+    n, c = x.shape[:2]
+    hw = x.numel() // (n * c)
+    y = torch.empty_like(x)
+    mean = torch.empty(n * G, device=x.device, dtype=torch.float32)
+    rstd = torch.empty_like(mean)
+    if gamma is not None:
+        gamma, beta = gamma.contiguous(), beta.contiguous()
+    check(lib().ddg_groupnorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), n, c, hw, G, eps,
+                                  int(per_sample), act, stream()), 'groupnorm_fwd')
+    return y, mean, rstd
+
+
+def groupnorm_bwd(x, dy, G, mean, rstd, gamma=None, beta=None, per_sample=False, act=ACT_NONE, need_affine_grads=True):
+    require_cuda_f32(x, dy, gamma, beta, mean, rstd)
+    x, dy = x.contiguous(), dy.contiguous()
+    n, c = x.shape[:2]
+    hw = x.numel() // (n * c)
+    dx = torch.empty_like(x)
+    dg = torch.empty(n, c, device=x.device, dtype=torch.float32) if need_affine_grads else None
+    db = torch.empty(n, c, device=x.device, dtype=torch.float32) if need_affine_grads else None
+    check(lib().ddg_groupnorm_bwd(ptr(x), ptr(dy), ptr(gamma), ptr(beta), ptr(mean), ptr(rstd), ptr(dx), ptr(dg), ptr(db),
+                                  n, c, hw, G, int(per_sample), act, stream()), 'groupnorm_bwd')
+    return dx, dg, db
+
+
+# ---------------------------------------------------------------------------------------------------------
+# small fused kernels
+# ---------------------------------------------------------------------------------------------------------
+def timestep_embedding(t: torch.Tensor, dim: int, max_positions: float = 10000.0, out=None) -> torch.Tensor:
+    assert t.is_cuda and t.dtype == torch.int64
+    if out is None:
+        out = torch.empty(t.shape[0], dim, device=t.device, dtype=torch.float32)
+    check(lib().ddg_timestep_embedding(ptr(t), ptr(out), t.shape[0], dim, float(max_positions), stream()), 'timestep_embedding')
+    return out
+
+
+def linear(x, W, b=None, act_in=ACT_NONE, act_out=ACT_NONE, pixel_norm=False, out=None):
+    """y = act_out(act_in(x) @ W.T + b); x [N, K] (row pitch = stride(0)), W [J, K]."""
+    require_cuda_f32(x, W, b)
+    assert x.stride(1) == 1 and W.is_contiguous()
+    n, k = x.shape
+    j = W.shape[0]
+    if out is None:
+        out = torch.empty(n, j, device=x.device, dtype=torch.float32)
+    assert out.stride(1) == 1
+    check(lib().ddg_linear(ptr(x), ptr(W), ptr(b), ptr(out), n, k, j, x.stride(0), out.stride(0), act_in, act_out,
+                           int(pixel_norm), stream()), 'linear')
+    return out
+
+
+def q_sample_pairs(x0, noise_xt, noise_xtp1, t, a_s_cum, sigmas_cum, a_s, sigmas, out=None):
+    require_cuda_f32(x0, noise_xt, noise_xtp1, a_s_cum, sigmas_cum, a_s, sigmas)
+    x0, noise_xt, noise_xtp1 = x0.contiguous(), noise_xt.contiguous(), noise_xtp1.contiguous()
+    x_t, x_tp1 = out if out is not None else (torch.empty_like(x0), torch.empty_like(x0))
+    n = x0.shape[0]
+    check(lib().ddg_q_sample_pairs(ptr(x0), ptr(noise_xt), ptr(noise_xtp1), ptr(t), ptr(a_s_cum), ptr(sigmas_cum), ptr(a_s),
+                                   ptr(sigmas), ptr(x_t), ptr(x_tp1), n, x0.numel() // n, stream()), 'q_sample_pairs')
+    return x_t, x_tp1
+
+
+def sample_posterior(x0, x_t, noise, t, coef1, coef2, logvar, out=None):
+    require_cuda_f32(x0, x_t, noise, coef1, coef2, logvar)
+    x0, x_t, noise = x0.contiguous(), x_t.contiguous(), noise.contiguous()
+    if out is None:
+        out = torch.empty_like(x_t)
+    n = x_t.shape[0]
+    check(lib().ddg_sample_posterior(ptr(x0), ptr(x_t), ptr(noise), ptr(t), ptr(coef1), ptr(coef2), ptr(logvar), ptr(out), n,
+                                     x_t.numel() // n, stream()), 'sample_posterior')
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# internal layout (PNHWC) helpers
+# ---------------------------------------------------------------------------------------------------------
+def alloc_pnhwc(n, h, w, c, device) -> torch.Tensor:
+    """Zero-initialised [N, H+2, W+2, C]; kernels only ever write the interior so the border stays zero."""
+    return torch.zeros(n, h + 2, w + 2, c, device=device, dtype=torch.float32)
+
+
+def to_pnhwc(a, b=None, cpad=None, out=None, scale=1.0, shift=0.0):
+    require_cuda_f32(a, b)
+    a = a.contiguous()
+    n, ca, h, w = a.shape
+    cb = 0
+    if b is not None:
+        b = b.contiguous()
+        cb = b.shape[1]
+    if cpad is None:
+        cpad = pad_c(ca + cb)
+    if out is None:
+        out = alloc_pnhwc(n, h, w, cpad, a.device)
+    check(lib().ddg_nchw_to_pnhwc(ptr(a), ca, ptr(b), cb, ptr(out), n, h, w, cpad, scale, shift, stream()), 'nchw_to_pnhwc')
+    return out
+
+
+def from_pnhwc(x, c=None, padded=True, out=None):
+    require_cuda_f32(x)
+    if padded:
+        n, hp, wp, cp = x.shape
+        h, w = hp - 2, wp - 2
+    else:
+        n, h, w, cp = x.shape
+    c = c or cp
+    if out is None:
+        out = torch.empty(n, c, h, w, device=x.device, dtype=torch.float32)
+    check(lib().ddg_pnhwc_to_nchw(ptr(x), ptr(out), n, h, w, c, cp, int(padded), stream()), 'pnhwc_to_nchw')
+    return out
+
+
+def gn_prepare(stats_a, ca, stats_b, cb, gamma, beta, gb_stride, per_sample, n, hw, groups, scale, shift, eps=1e-6):
+    check(lib().ddg_gn_prepare(ptr(stats_a), ca, ptr(stats_b), cb, ptr(gamma), ptr(beta), gb_stride, int(per_sample),
+                               ptr(scale), ptr(shift), n, hw, groups, eps, stream()), 'gn_prepare')
+
+
+def fir_pnhwc(x, mode, out, scale=None, shift=None, act=ACT_NONE):
+    """mode 1 up2, 2 down2, 3 pad(2,2)+space-to-depth.  x [N,H+2,W+2,C]."""
+    n, hp, wp, c = x.shape
+    check(lib().ddg_fir_pnhwc(ptr(x), ptr(scale), ptr(shift), act, ptr(out), n, hp - 2, wp - 2, c, mode, out.shape[-1], None,
+                              stream()), 'fir_pnhwc')
+    return out
+
+
+def minibatch_stddev(x, out, group):
+    n, hp, wp, c = x.shape
+    check(lib().ddg_minibatch_stddev(ptr(x), ptr(out), n, hp - 2, wp - 2, c, out.shape[-1], group, stream()), 'minibatch_stddev')
+    return out
+
+
+def spatial_sum(x, act=ACT_NONE, out=None):
+    n, hp, wp, c = x.shape
+    if out is None:
+        out = torch.empty(n, c, device=x.device, dtype=torch.float32)
+    check(lib().ddg_spatial_sum(ptr(x), ptr(out), n, hp - 2, wp - 2, c, act, stream()), 'spatial_sum')
+    return out
+
+
+def softmax_rows(s, p, rows, T, lds, ldp):
+    check(lib().ddg_softmax_rows(ptr(s), ptr(p), rows, T, lds, ldp, stream()), 'softmax_rows')
+    return p
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tcgen05 implicit-GEMM convolution
+# ---------------------------------------------------------------------------------------------------------
+class ConvWeights:
+    """Device-resident packed B operand of one fused convolution (all K segments, all n-tiles).
+
+    segs: list of (C_padded, ntaps).  Call pack_segment() for each segment whenever the fp32 weights change."""
+
+    def __init__(self, cout: int, segs, device, precision: int = 3, batch: int = 1):
+        self.cout = cout
+        self.segs = list(segs)
+        self.precision = precision
+        self.batch = batch
+        self.total_stages = sum((c // KB) * nt for c, nt in self.segs)
+        self.bytes_per_batch = lib().ddg_conv_packed_bytes(cout, self.total_stages, KB, precision)
+        self.buf = torch.empty(self.bytes_per_batch * batch, dtype=torch.uint8, device=device)
+        self.offsets = []
+        off = 0
+        for c, nt in self.segs:
+            self.offsets.append(off)
+            off += (c // KB) * nt
+
+    def pack_segment(self, i: int, w: torch.Tensor, cin_real: int, s_co: int, s_ci: int, s_tap: int, flip: bool = False,
+                     w_batch_stride: int = 0):
+        require_cuda_f32(w)
+        c, nt = self.segs[i]
+        check(lib().ddg_conv_pack_weights(ptr(w), ptr(self.buf), self.cout, cin_real, c, nt, s_co, s_ci, s_tap, int(flip),
+                                          KB, self.offsets[i], self.total_stages, self.precision, self.batch, w_batch_stride,
+                                          stream()), 'conv_pack_weights')
+
+    def pack_conv_weight(self, i: int, w: torch.Tensor):
+        """w: [Cout, Cin, kh, kw] contiguous (nn.Conv2d layout)."""
+        assert w.is_contiguous()
+        co, ci, kh, kw = w.shape
+        assert kh * kw == self.segs[i][1] and co == self.cout
+        self.pack_segment(i, w, ci, ci * kh * kw, kh * kw, 1)
+
+    def pack_nin_weight(self, i: int, W: torch.Tensor):
+        """W: [in, out] contiguous (layers.py:492 NIN)."""
+        assert W.is_contiguous() and W.shape[1] == self.cout
+        self.pack_segment(i, W, W.shape[0], 1, W.shape[1], 0)
+
+
+def conv_src(x, c, taps, scale=None, shift=None, act=ACT_NONE, padded=True):
+    return dict(x=x, C=c, taps=taps, scale=scale, shift=shift, act=act, padded=padded)
+
+
+def build_conv_desc(weights: ConvWeights, srcs, n, hout, wout, out, out_mode=OUT_PNHWC, hp=None, wp=None, bias=None, addvec=None,
+                    addvec_stride=0, res=None, out_scale=1.0, out_act=ACT_NONE, out_c=0, stats=None, msub=0, batch_rows=0,
+                    debug_swap=0) -> ConvDesc:
+    d = ConvDesc()
+    d.nsrc = len(srcs)
+    for i, s in enumerate(srcs):
+        sd = d.src[i]
+        sd.x = ptr(s['x']); sd.scale = ptr(s.get('scale')); sd.shift = ptr(s.get('shift'))
+        sd.C = s['C']; sd.act = s.get('act', ACT_NONE); sd.ntaps = len(s['taps']); sd.padded = int(s.get('padded', True))
+        for t, (dr, ds) in enumerate(s['taps']):
+            sd.tap_dr[t] = dr
+            sd.tap_ds[t] = ds
+        assert (s['C'], len(s['taps'])) == tuple(weights.segs[i]), 'source / packed-weight segment mismatch'
+    d.wpack = ptr(weights.buf)
+    d.kb = KB
+    d.N, d.Hout, d.Wout = n, hout, wout
+    d.Hp = hp if hp is not None else hout + 2
+    d.Wp = wp if wp is not None else wout + 2
+    d.Cout = weights.cout
+    d.bias = ptr(bias); d.addvec = ptr(addvec); d.addvec_stride = addvec_stride
+    d.res = ptr(res); d.out_scale = out_scale; d.out_act = out_act
+    d.out = ptr(out); d.out_mode = out_mode; d.out_C = out_c
+    d.stats = ptr(stats)
+    d.precision = weights.precision
+    d.msub = msub
+    d.batch_rows = batch_rows
+    d.debug_swap_lbo_sbo = debug_swap
+    return d
+
+
+def conv_launch(desc: ConvDesc):
+    check(lib().ddg_conv2d_fwd(C.byref(desc), stream()), 'conv2d_fwd')
+
+
+def conv2d_fused(weights, srcs, n, hout, wout, out, **kw):
+    d = build_conv_desc(weights, srcs, n, hout, wout, out, **kw)
+    conv_launch(d)
+    return out

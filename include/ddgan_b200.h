@@ -1,0 +1,147 @@
+/* ddgan_b200 -- C ABI of the B200-native DDGAN hot path (libddgan_b200.so).
+ *
+ * Every entry point takes plain device pointers, sizes and a cudaStream_t; none allocates, synchronises or throws.
+ * Return value: 0 = ok, <0 = error (ddg_last_error() gives the text).  All tensors are fp32 unless stated.
+ * The reference interface each function replaces is cited as file:line under /root/reference.
+ *
+ * Internal activation layout ("PNHWC"): [N][H+2][W+2][C] fp32 with an all-zero one-pixel border, C a multiple of 32.
+ * Public operator surface (score_sde.op.*) is NCHW like the reference.
+ */
+#ifndef DDGAN_B200_H
+#define DDGAN_B200_H
+
+#include <stdint.h>
+#ifndef __CUDACC__
+typedef struct CUstream_st* cudaStream_t;
+#else
+#include <cuda_runtime.h>
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* ddg_last_error(void);
+int ddg_version(void);
+
+/* ---- score_sde/op/upfirdn2d.cpp:20-31 (upfirdn2d_op.upfirdn2d) + upfirdn2d_kernel.cu:211-371 -------------------
+ * x: [planes][in_h][in_w] (planes = N*C, minor = 1 as the Python layer always passes, upfirdn2d.py:107),
+ * k: [kh][kw] on device.  out: [planes][out_h][out_w], out_h = (in_h*up_y + pad_y0 + pad_y1 - kh)/down_y + 1.
+ * The adjoint (UpFirDn2dBackward, upfirdn2d.py:27-68) and the double-backward (:70-93) are the same entry with
+ * up/down swapped and the g_pad arithmetic of upfirdn2d.py:119-122 done by the caller. */
+int ddg_upfirdn2d(const float* x, const float* k, float* out, long planes, int in_h, int in_w, int kh, int kw,
+                  int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                  cudaStream_t stream);
+int ddg_upfirdn2d_out_size(int in_size, int up, int down, int pad0, int pad1, int ksize);
+
+/* ---- score_sde/op/fused_bias_act.cpp:18-28 (fused.fused_bias_act), fused_bias_act_kernel.cu:20-101 --------------
+ * y = f(x + b[(i / step_b) % size_b]) * scale; act=3 (leaky relu): grad=0 -> f = lrelu(alpha); grad=1 -> gate by
+ * ref > 0; grad=2 -> 0.  act=1 linear.  b / ref may be NULL ("empty tensor" in the reference). */
+int ddg_fused_bias_act(const float* x, const float* b, const float* ref, float* y, long n, int step_b, int size_b,
+                       int act, int grad, float alpha, float scale, cudaStream_t stream);
+/* grad_bias of FusedLeakyReLUFunctionBackward (fused_act.py:42-47): out[c] = sum over n, spatial of g[n][c][...] */
+int ddg_channel_sum(const float* g, float* out, int N, int C, int inner, cudaStream_t stream);
+
+/* ---- nn.GroupNorm / AdaptiveGroupNorm (layerspp.py:46-63, :100; ncsnpp_generator_adagn.py:264), NCHW ------------
+ * y = act(gamma[n,c] * (x - mean)/sqrt(var+eps) + beta[n,c]); gamma/beta: per-(n,c) (stride C) when per_sample=1,
+ * per-channel when 0, NULL = identity.  mean/rstd [N*G] are written (needed by the backward). */
+int ddg_groupnorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, int N,
+                      int C, int HW, int G, float eps, int per_sample, int act, cudaStream_t stream);
+/* backward: dx, and (optional) dgamma/dbeta reduced over HW per (n,c) -- the caller reduces over n for affine GN. */
+int ddg_groupnorm_bwd(const float* x, const float* dy, const float* gamma, const float* beta, const float* mean,
+                      const float* rstd, float* dx, float* dgamma_nc, float* dbeta_nc, int N, int C, int HW, int G,
+                      int per_sample, int act, cudaStream_t stream);
+
+/* ---- fused small kernels -------------------------------------------------------------------------------------
+ * layers.py:475-486 get_timestep_embedding: out[n][j] = sin|cos(t[n] * exp(-j ln(max_pos)/(half-1))) */
+int ddg_timestep_embedding(const int64_t* t, float* out, int N, int dim, float max_positions, cudaStream_t stream);
+/* y[n][j] = act_out( sum_k act_in(x[n][k]) * W[j][k] + b[j] ), nn.Linear layout W [out][in].  pixel_norm=1 applies
+ * ncsnpp_generator_adagn.py:51-56 (x / sqrt(mean(x^2)+1e-8)) to the input row first.  Used for the z-mapping MLP
+ * (:271-277), the temb MLP (:301-303), AdaGN style projections (layerspp.py:57) and Dense_0 (:298-299). */
+int ddg_linear(const float* x, const float* W, const float* b, float* y, int N, int K, int J, int ldx, int ldy, int act_in,
+               int act_out, int pixel_norm, cudaStream_t stream);
+/* ddgan.py:110-126 q_sample_pairs with injected noise: x_t = a_cum[t] x0 + s_cum[t] n0 ; x_tp1 = a[t+1] x_t + s[t+1] n1 */
+int ddg_q_sample_pairs(const float* x0, const float* noise_xt, const float* noise_xtp1, const int64_t* t, const float* a_s_cum,
+                       const float* sigmas_cum, const float* a_s, const float* sigmas, float* x_t, float* x_tp1, int N,
+                       long per_sample, cudaStream_t stream);
+/* ddgan.py:152-169 / test_ddgan.py:96-113 sample_posterior with injected noise */
+int ddg_sample_posterior(const float* x0, const float* x_t, const float* noise, const int64_t* t, const float* coef1,
+                         const float* coef2, const float* logvar, float* out, int N, long per_sample, cudaStream_t stream);
+
+/* ---- internal layout helpers ---------------------------------------------------------------------------------
+ * NCHW sources (up to 2, concatenated along C: discriminator.py:138 cat(x, x_t)) -> PNHWC with C padded to Cpad. */
+int ddg_nchw_to_pnhwc(const float* a, int Ca, const float* b, int Cb, float* out, int N, int H, int W, int Cpad,
+                      float scale, float shift, cudaStream_t stream);
+int ddg_pnhwc_to_nchw(const float* x, float* out, int N, int H, int W, int C, int Cpitch, int padded, cudaStream_t stream);
+/* AdaGN / GN prologue coefficients from per-(n,c) sums written by the conv epilogue:
+ *   scale[n,c] = gamma*rstd ; shift[n,c] = beta - mean*gamma*rstd, groups over the concatenation of up to two
+ *   sources (ncsnpp_generator_adagn.py:367 torch.cat([h, hs.pop()])).  gamma/beta as in ddg_groupnorm_fwd. */
+int ddg_gn_prepare(const double* stats_a, int Ca, const double* stats_b, int Cb, const float* gamma, const float* beta,
+                   int gb_stride, int per_sample, float* scale, float* shift, int N, int HW, int G, float eps,
+                   cudaStream_t stream);
+/* FIR resampling on PNHWC with the AdaGN+SiLU prologue fused on load (layerspp.py:279-293): [1,3,3,1] (x) [1,3,3,1]
+ * mode 1: up x2 (upsample_2d, up_or_down_sampling.py:200-228), mode 2: down x2 (downsample_2d, :231-261),
+ * mode 3: pad (2,2) FIR (H -> H+1) written space-to-depth for the stride-2 conv of conv_downsample_2d (:149-183):
+ *         out [N][Ho+3][Wo+3][4*C -> Cout_pitch], Ho = H/2, cell (i,j) channel (py*2+px)*C + c = fir[2i+py][2j+px][c]. */
+int ddg_fir_pnhwc(const float* x, const float* scale, const float* shift, int act, float* out, int N, int H, int W, int C,
+                  int mode, int out_pitch, double* stats, cudaStream_t stream);
+/* minibatch stddev feature (discriminator.py:150-158) from a PNHWC tensor -> PNHWC [N][H+2][W+2][Cpad] channel 0 */
+int ddg_minibatch_stddev(const float* x, float* out, int N, int H, int W, int C, int Cpad, int group, cudaStream_t stream);
+/* out[n][c] = sum_{h,w} act(x[n][h][w][c]) over the interior of a PNHWC tensor (discriminator.py:163-165) */
+int ddg_spatial_sum(const float* x, float* out, int N, int H, int W, int C, int act, cudaStream_t stream);
+/* row softmax of the attention logits (layerspp.py:116-118): p[r][0:T] = softmax(s[r][0:T]), p[r][T:ldp] = 0 */
+int ddg_softmax_rows(const float* s, float* p, long rows, int T, int lds, int ldp, cudaStream_t stream);
+
+/* ---- implicit-GEMM convolution on tcgen05 / TMEM (replaces nn.Conv2d -> cuDNN: layers.py:114-138,
+ *      dense_layer.py:73-80, NIN layers.py:489-512, up_or_down_sampling.py:56,183) -------------------------------- */
+#define DDG_CONV_MAX_SRC 3
+typedef struct {
+  const float* x;      /* PNHWC (padded=1) or NHWC (padded=0) source, channel pitch C */
+  const float* scale;  /* [N][C] prologue scale or NULL */
+  const float* shift;  /* [N][C] prologue shift or NULL */
+  int C;               /* channels, multiple of kb */
+  int act;             /* prologue activation: 0 none, 1 SiLU, 2 LeakyReLU(0.2) */
+  int ntaps;           /* taps this source contributes (9 = 3x3, 4 = 2x2, 1 = 1x1) */
+  int padded;
+  int8_t tap_dr[9];    /* row / column offset of every tap relative to the output position */
+  int8_t tap_ds[9];
+} ddg_conv_src;
+
+typedef struct {
+  ddg_conv_src src[DDG_CONV_MAX_SRC]; /* K segments, consumed in order (concat inputs / fused 1x1 skip conv) */
+  int nsrc;
+  const void* wpack;   /* ddg_conv_pack_weights output */
+  int kb;              /* K block (32) */
+  int N, Hout, Wout;   /* output image size */
+  int Hp, Wp;          /* padded input space (any source with ntaps > 1): Hout+2 x Wout+2 for 3x3 pad 1 */
+  int Cout;
+  const float* bias;   /* [Cout] or NULL */
+  const float* addvec; /* [N][addvec_stride] per-sample per-channel add (Dense_0(temb)) or NULL */
+  int addvec_stride;
+  const float* res;    /* residual, same layout as out, or NULL */
+  float out_scale;     /* applied after the residual add (1/sqrt2 for skip_rescale) */
+  int out_act;         /* 0 none, 3 tanh */
+  float* out;
+  int out_mode;        /* 0 PNHWC, 1 NHWC, 2 NCHW */
+  int out_C;           /* channel pitch of out/res for NHWC modes (0 = Cout) */
+  double* stats;       /* [N][Cout][2] running sum / sum of squares of the stored values, or NULL */
+  int precision;       /* 3 = BF16x3 split (fp32 parity), 1 = plain BF16 */
+  int msub;            /* 0 auto, 1 or 2 accumulators of 128 rows per CTA */
+  int batch_rows;      /* >0: batched GEMM (1x1 only): rows [b*batch_rows, (b+1)*batch_rows) use packed operand b
+                          (wpack + b * ddg_conv_packed_bytes(...)); used for the attention GEMMs (layerspp.py:115-119) */
+  int debug_swap_lbo_sbo;
+} ddg_conv_desc;
+
+int ddg_conv_tile_n(int cout);
+long ddg_conv_packed_bytes(int cout, int total_stages, int kb, int precision);
+/* w[co*s_co + ci*s_ci + tap*s_tap] -> packed stages [stage_offset, stage_offset + cin_pad/kb*ntaps) of every n-tile */
+/* batch > 1: `batch` operands, w advances by w_batch_stride floats, out by ddg_conv_packed_bytes(...) bytes per batch */
+int ddg_conv_pack_weights(const float* w, void* out, int cout, int cin_real, int cin_pad, int ntaps, long s_co, long s_ci,
+                          long s_tap, int flip_taps, int kb, int stage_offset, int total_stages, int precision, int batch,
+                          long w_batch_stride, cudaStream_t stream);
+int ddg_conv2d_fwd(const ddg_conv_desc* desc, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

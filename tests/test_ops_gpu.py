@@ -1,0 +1,261 @@
+"""GPU parity of every C-ABI kernel against the CPU oracle (bit-for-tolerance: fp32 path <= 1e-4 relative L2,
+north_star).  All calls go through libddgan_b200.so via ddgan_b200.ops."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ddgan_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # north_star: FP32 mode within 1e-4 relative L2 per op
+DEV = 'cuda'
+
+
+def seeded(shape, seed, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from ddgan_b200 import ops as _ops
+    return _ops
+
+
+def test_upfirdn2d_golden_cases(ops, golden):
+    for c in golden['upfirdn2d_cases']:
+        x = seeded(c['shape'], c['seed'])
+        n, ch, h, w = x.shape
+        y = ops.upfirdn2d_raw(x.view(n * ch, h, w).to(DEV), c['kernel'].to(DEV), c['up'], c['up'], c['down'], c['down'],
+                              c['pad'][0], c['pad'][1], c['pad'][0], c['pad'][1])
+        ref = c['out']
+        assert tuple(y.shape[1:]) == tuple(ref.shape[2:]), c['name']
+        assert O.rel_l2(y.view(ref.shape).cpu(), ref) < 1e-6, c['name']
+
+
+@pytest.mark.parametrize('shape,up,down,pad', [((64, 128, 32, 32), 1, 2, (1, 1)), ((64, 256, 16, 16), 2, 1, (2, 1)),
+                                               ((8, 3, 32, 32), 1, 1, (2, 2)), ((2, 4, 33, 31), 2, 1, (2, 1)),
+                                               ((1, 1, 1, 1), 2, 1, (2, 1)), ((2, 3, 5, 7), 1, 2, (1, 1))])
+def test_upfirdn2d_cifar_shapes(ops, shape, up, down, pad):
+    x = seeded(shape, 1)
+    k = torch.from_numpy(O.setup_fir_kernel([1, 3, 3, 1])) * (up ** 2)
+    n, c, h, w = shape
+    y = ops.upfirdn2d_raw(x.view(n * c, h, w).to(DEV), k.to(DEV), up, up, down, down, pad[0], pad[1], pad[0], pad[1])
+    ref = O.upfirdn2d(x, k, up, down, pad)
+    assert O.rel_l2(y.view(ref.shape).cpu(), ref) < 1e-6
+
+
+def test_fused_bias_act(ops):
+    x = seeded((4, 16, 8, 8), 2); b = seeded((16,), 3)
+    y = ops.fused_bias_act(x.to(DEV), b.to(DEV), None, 3, 0, 0.2, 2 ** 0.5)
+    assert O.rel_l2(y.cpu(), O.fused_leaky_relu(x, b)) < 1e-6
+    # other slope, odd spatial size (scalar path)
+    x = seeded((3, 5, 3, 3), 4); b = seeded((5,), 5)
+    y = ops.fused_bias_act(x.to(DEV), b.to(DEV), None, 3, 0, 0.1, 1.5)
+    assert O.rel_l2(y.cpu(), O.fused_leaky_relu(x, b, 0.1, 1.5)) < 1e-6
+    # gradient mode (fused_act.py:28-50)
+    out = O.fused_leaky_relu(x, b, 0.1, 1.5); g = seeded(tuple(x.shape), 6)
+    gi = ops.fused_bias_act(g.to(DEV), None, out.to(DEV), 3, 1, 0.1, 1.5)
+    gref, gb = O.fused_leaky_relu_grad(g, out, 0.1, 1.5)
+    assert O.rel_l2(gi.cpu(), gref) < 1e-6
+    assert O.rel_l2(ops.channel_sum(gi).cpu(), gb) < 1e-5
+    # empty input
+    assert ops.fused_bias_act(torch.empty(0, 4, device=DEV), None, None, 3, 0, 0.2, 1.0).numel() == 0
+
+
+@pytest.mark.parametrize('n,c,h,act,ada', [(4, 128, 32, 1, True), (2, 256, 16, 0, False), (3, 384, 8, 1, True),
+                                           (2, 12, 5, 0, True), (2, 64, 64, 1, True)])
+def test_groupnorm_fwd_bwd(ops, n, c, h, act, ada):
+    x = seeded((n, c, h, h), 7) * 2 + 0.5
+    G = O.num_groups(c)
+    if ada:
+        gamma = 1 + seeded((n, c), 8) * 0.2; beta = seeded((n, c), 9) * 0.2
+    else:
+        gamma = 1 + seeded((c,), 8) * 0.2; beta = seeded((c,), 9) * 0.2
+    xr = x.clone().requires_grad_(True); gr = gamma.clone().requires_grad_(True); br = beta.clone().requires_grad_(True)
+    y0 = O.group_norm(xr, G)
+    if ada:
+        ref = gr[:, :, None, None] * y0 + br[:, :, None, None]
+    else:
+        ref = gr.view(1, -1, 1, 1) * y0 + br.view(1, -1, 1, 1)
+    if act == 1:
+        ref = F.silu(ref)
+    y, mean, rstd = ops.groupnorm_fwd(x.to(DEV), G, gamma.to(DEV), beta.to(DEV), per_sample=ada, act=act)
+    assert O.rel_l2(y.cpu(), ref) < 1e-5
+    dy = seeded(tuple(x.shape), 10)
+    ref.backward(dy)
+    dx, dg, db = ops.groupnorm_bwd(x.to(DEV), dy.to(DEV), G, mean, rstd, gamma.to(DEV), beta.to(DEV), per_sample=ada, act=act)
+    assert O.rel_l2(dx.cpu(), xr.grad) < TOL
+    if ada:
+        assert O.rel_l2(dg.cpu(), gr.grad) < TOL and O.rel_l2(db.cpu(), br.grad) < TOL
+    else:
+        assert O.rel_l2(dg.sum(0).cpu(), gr.grad) < TOL and O.rel_l2(db.sum(0).cpu(), br.grad) < TOL
+
+
+def test_small_kernels(ops):
+    t = torch.tensor([0, 1, 2, 3, 3, 0])
+    for dim in (128, 256, 32):
+        e = ops.timestep_embedding(t.to(DEV), dim)
+        assert O.rel_l2(e.cpu(), O.timestep_embedding(t, dim)) < 1e-6
+    x = seeded((70, 100), 11); W = seeded((256, 100), 12, 0.1); b = seeded((256,), 13)
+    zn = x / torch.sqrt(torch.mean(x ** 2, dim=1, keepdim=True) + 1e-8)
+    y = ops.linear(x.to(DEV), W.to(DEV), b.to(DEV), act_out=ops.ACT_SILU, pixel_norm=True)
+    assert O.rel_l2(y.cpu(), F.silu(F.linear(zn, W, b))) < 1e-5
+    x = seeded((64, 512), 14); W = seeded((300, 512), 15, 0.05)
+    y = ops.linear(x.to(DEV), W.to(DEV), None, act_in=ops.ACT_SILU)
+    assert O.rel_l2(y.cpu(), F.linear(F.silu(x), W)) < 1e-5
+    cfg = O.cifar10_config()
+    co, pc = O.diffusion_coefficients(cfg), O.posterior_coefficients(cfg)
+    x0 = seeded((6, 3, 32, 32), 16); n0 = seeded((6, 3, 32, 32), 17); n1 = seeded((6, 3, 32, 32), 18)
+    xt, xtp1 = ops.q_sample_pairs(x0.to(DEV), n0.to(DEV), n1.to(DEV), t.to(DEV), co.a_s_cum.to(DEV), co.sigmas_cum.to(DEV),
+                                  co.a_s.to(DEV), co.sigmas.to(DEV))
+    rt, rtp1 = O.q_sample_pairs(co, x0, t, n0, n1)
+    assert O.rel_l2(xt.cpu(), rt) < 1e-6 and O.rel_l2(xtp1.cpu(), rtp1) < 1e-6
+    xp = ops.sample_posterior(x0.to(DEV), n0.to(DEV), n1.to(DEV), t.to(DEV), pc.posterior_mean_coef1.to(DEV),
+                              pc.posterior_mean_coef2.to(DEV), pc.posterior_log_variance_clipped.to(DEV))
+    assert O.rel_l2(xp.cpu(), O.sample_posterior(pc, x0, n0, t, n1)) < 1e-6
+    # ragged (non multiple of 4) size takes the scalar path
+    x0 = seeded((3, 1, 5, 5), 19); n0 = seeded((3, 1, 5, 5), 20); n1 = seeded((3, 1, 5, 5), 21); t3 = torch.tensor([0, 2, 3])
+    xp = ops.sample_posterior(x0.to(DEV), n0.to(DEV), n1.to(DEV), t3.to(DEV), pc.posterior_mean_coef1.to(DEV),
+                              pc.posterior_mean_coef2.to(DEV), pc.posterior_log_variance_clipped.to(DEV))
+    assert O.rel_l2(xp.cpu(), O.sample_posterior(pc, x0, n0, t3, n1)) < 1e-6
+
+
+def test_layout_roundtrip_and_fir(ops):
+    a = seeded((3, 3, 8, 8), 22); b = seeded((3, 3, 8, 8), 23)
+    p = ops.to_pnhwc(a.to(DEV), b.to(DEV), cpad=32)
+    assert p.shape == (3, 10, 10, 32)
+    back = ops.from_pnhwc(p, 6)
+    assert torch.equal(back.cpu(), torch.cat([a, b], 1))
+    assert float(p[:, 0].abs().max()) == 0 and float(p[..., 6:].abs().max()) == 0
+    # FIR on PNHWC with fused affine + SiLU
+    x = seeded((2, 32, 8, 8), 24); sc = 0.5 + torch.rand(2, 32, generator=torch.Generator().manual_seed(1)); sh = seeded((2, 32), 25, 0.3)
+    xp = ops.to_pnhwc(x.to(DEV))
+    tr = F.silu(x * sc[:, :, None, None] + sh[:, :, None, None])
+    up = ops.fir_pnhwc(xp, 1, ops.alloc_pnhwc(2, 16, 16, 32, DEV), sc.to(DEV), sh.to(DEV), ops.ACT_SILU)
+    assert O.rel_l2(ops.from_pnhwc(up).cpu(), O.upsample_2d(tr)) < 1e-5
+    dn = ops.fir_pnhwc(xp, 2, ops.alloc_pnhwc(2, 4, 4, 32, DEV))
+    assert O.rel_l2(ops.from_pnhwc(dn).cpu(), O.downsample_2d(x)) < 1e-5
+    # mode 3: pad(2,2) FIR stored space-to-depth: cell (i,j), block (py,px) = fir[2i+py][2j+px]
+    s2d = ops.fir_pnhwc(xp, 3, torch.zeros(2, 4 + 3, 4 + 3, 128, device=DEV))
+    k = torch.from_numpy(O.setup_fir_kernel([1, 3, 3, 1]))
+    fir = O.upfirdn2d(x, k, pad=(2, 2))  # [2, 32, 9, 9]
+    firp = F.pad(fir, (0, 1, 0, 1))      # 10 x 10, zero at index 9
+    cells = firp.view(2, 32, 5, 2, 5, 2).permute(0, 2, 4, 3, 5, 1).reshape(2, 5, 5, 128)
+    assert O.rel_l2(s2d[:, 1:6, 1:6, :].cpu(), cells) < 1e-5
+
+
+def _conv_case(ops, n, cin, cout, h, k, prec=3, affine=False, act=0, res=False, nchw=False, msub=0, temb=False, skip1x1=0):
+    x = seeded((n, cin, h, h), 30)
+    w = seeded((cout, cin, k, k), 31) / math.sqrt(cin * k * k)
+    b = seeded((cout,), 32, 0.1)
+    xin = x
+    sc = sh = None
+    if affine:
+        sc = torch.rand(n, cin, generator=torch.Generator().manual_seed(2)) + 0.5; sh = seeded((n, cin), 33, 0.3)
+        xin = x * sc[:, :, None, None] + sh[:, :, None, None]
+    if act == 1:
+        xin = F.silu(xin)
+    elif act == 2:
+        xin = F.leaky_relu(xin, 0.2)
+    ref = F.conv2d(xin, w, b, padding=k // 2)
+    tv = None
+    if temb:
+        tv = seeded((n, cout), 34)
+        ref = ref + tv[:, :, None, None]
+    cp = ops.pad_c(cin)
+    taps = ops.TAPS_3X3 if k == 3 else ops.TAPS_1X1
+    segs = [(cp, len(taps))]
+    srcs = []
+    xs = w2 = None
+    if skip1x1:
+        xs = seeded((n, skip1x1, h, h), 35); w2 = seeded((cout, skip1x1, 1, 1), 36) / math.sqrt(skip1x1)
+        ref = ref + F.conv2d(xs, w2)
+        segs.append((ops.pad_c(skip1x1), 1))
+    r = None
+    if res:
+        r = seeded((n, cout, h, h), 37)
+        ref = (ref + r) / math.sqrt(2)
+    cw = ops.ConvWeights(cout, segs, DEV, precision=prec)
+    cw.pack_conv_weight(0, w.to(DEV).contiguous())
+    scd = shd = None
+    if affine:
+        scd = torch.zeros(n, cp, device=DEV); scd[:, :cin] = sc.to(DEV)
+        shd = torch.zeros(n, cp, device=DEV); shd[:, :cin] = sh.to(DEV)
+    srcs.append(ops.conv_src(ops.to_pnhwc(x.to(DEV), cpad=cp), cp, taps, scale=scd, shift=shd, act=act))
+    if skip1x1:
+        cw.pack_conv_weight(1, w2.to(DEV).contiguous())
+        srcs.append(ops.conv_src(ops.to_pnhwc(xs.to(DEV)), ops.pad_c(skip1x1), ops.TAPS_1X1))
+    st = torch.zeros(n, cout, 2, dtype=torch.float64, device=DEV)
+    if nchw:
+        out = torch.zeros(n, cout, h, h, device=DEV); mode = ops.OUT_NCHW
+        rd = r.to(DEV) if res else None
+    else:
+        out = ops.alloc_pnhwc(n, h, h, cout, DEV); mode = ops.OUT_PNHWC
+        rd = ops.to_pnhwc(r.to(DEV), cpad=cout) if res else None
+    ops.conv2d_fused(cw, srcs, n, h, h, out, out_mode=mode, bias=b.to(DEV), res=rd,
+                     out_scale=(1 / math.sqrt(2) if res else 1.0), stats=st, msub=msub,
+                     addvec=(tv.to(DEV) if temb else None), addvec_stride=cout)
+    y = out if nchw else ops.from_pnhwc(out, cout)
+    err = O.rel_l2(y.cpu(), ref)
+    s1 = ref.double().sum(dim=(2, 3)); s2 = (ref.double() ** 2).sum(dim=(2, 3))
+    e1 = float((st[:, :, 0].cpu() - s1).norm() / s2.sum().sqrt()); e2 = O.rel_l2(st[:, :, 1].cpu(), s2)
+    if not nchw:
+        border = out.clone(); border[:, 1:-1, 1:-1, :] = 0
+        assert float(border.abs().max()) == 0.0
+    return err, e1, e2
+
+
+@pytest.mark.parametrize('n,cin,cout,h,k', [(2, 32, 128, 8, 1), (2, 32, 128, 8, 3), (4, 64, 128, 16, 3), (8, 128, 256, 32, 3),
+                                            (4, 3, 128, 32, 3), (3, 512, 512, 4, 3), (5, 256, 64, 4, 1), (1, 128, 128, 32, 3)])
+def test_conv_tc_plain(ops, n, cin, cout, h, k):
+    err, e1, e2 = _conv_case(ops, n, cin, cout, h, k)
+    assert err < 2e-5 and e1 < 1e-5 and e2 < 1e-5, (err, e1, e2)
+
+
+def test_conv_tc_fused_variants(ops):
+    err, e1, e2 = _conv_case(ops, 4, 256, 256, 16, 3, affine=True, act=1, res=True, temb=True)
+    assert err < 2e-5 and e1 < 1e-5 and e2 < 1e-5, (err, e1, e2)
+    err, _, _ = _conv_case(ops, 4, 128, 3, 32, 3, nchw=True)
+    assert err < 2e-5
+    err, _, _ = _conv_case(ops, 2, 128, 128, 16, 3, act=2, msub=1)
+    assert err < 2e-5
+    err, _, _ = _conv_case(ops, 2, 128, 128, 16, 3, act=2, msub=2)
+    assert err < 2e-5
+    # fused 1x1 skip conv as a second K segment + residual rescale (ResnetBlockBigGANpp_Adagn, layerspp.py:305-310)
+    err, e1, e2 = _conv_case(ops, 4, 256, 128, 16, 3, affine=True, act=1, skip1x1=384)
+    assert err < 2e-5 and e1 < 1e-5 and e2 < 1e-5, (err, e1, e2)
+
+
+def test_conv_tc_bf16_mode(ops):
+    # BF16 mode: single-pass bf16 operands, fp32 accumulate.  Stated tolerance: 5e-3 relative L2 per op
+    # (SURVEY.md section 7 hard part 1 measured 2.3e-3 for bf16 operands).
+    err, _, _ = _conv_case(ops, 4, 128, 256, 16, 3, prec=1)
+    assert 1e-4 < err < 5e-3, err
+
+
+def test_batched_gemm_attention_core(ops):
+    # S = q k^T * C^-1/2 ; P = softmax(S) ; O = P v   (layerspp.py:115-119) through the batched 1x1 mode
+    n, T, c = 3, 64, 128
+    q = seeded((n, T, c), 40); k = seeded((n, T, c), 41); v = seeded((n, T, c), 42)
+    ref_s = torch.einsum('btc,bsc->bts', q, k) * (c ** -0.5)
+    ref_p = torch.softmax(ref_s, dim=-1)
+    ref_o = torch.einsum('bts,bsc->btc', ref_p, v)
+    qd, kd, vd = q.to(DEV), k.to(DEV), v.to(DEV)
+    wk = ops.ConvWeights(T, [(c, 1)], DEV, batch=n)
+    wk.pack_segment(0, kd, c, c, 1, 0, w_batch_stride=T * c)          # B[co = key][ci = channel]
+    Tp = ops.pad_c(T)
+    s = torch.zeros(n, T, Tp, device=DEV)
+    ops.conv2d_fused(wk, [ops.conv_src(qd, c, ops.TAPS_1X1, padded=False)], n, 1, T, s, out_mode=ops.OUT_NHWC, out_c=Tp,
+                     out_scale=c ** -0.5, batch_rows=T)
+    assert O.rel_l2(s[:, :, :T].cpu(), ref_s) < 2e-5
+    p = torch.empty_like(s)
+    ops.softmax_rows(s, p, n * T, T, Tp, Tp)
+    assert O.rel_l2(p[:, :, :T].cpu(), ref_p) < 2e-5
+    wv = ops.ConvWeights(c, [(Tp, 1)], DEV, batch=n)
+    wv.pack_segment(0, vd, T, 1, c, 0, w_batch_stride=T * c)          # B[co = channel][ci = key] = v[key][channel]
+    o = torch.zeros(n, T, c, device=DEV)
+    ops.conv2d_fused(wv, [ops.conv_src(p, Tp, ops.TAPS_1X1, padded=False)], n, 1, T, o, out_mode=ops.OUT_NHWC, batch_rows=T)
+    assert O.rel_l2(o.cpu(), ref_o) < 3e-5
