@@ -129,7 +129,9 @@ struct SrcDev {
   const float* x;
   const float* scale;
   const float* shift;
-  int C;          // channels of the source tensor (row pitch)
+  int C;          // channels contributed by this source
+  int pitch;      // row pitch of x in floats
+  int ss_stride;  // row pitch of scale / shift in floats
   int act;
   int ntaps;
   int padded;     // gather mode only: source is padded NHWC
@@ -159,7 +161,6 @@ struct ConvDev {
   int out_mode;                // 0 padded NHWC, 1 NHWC, 2 NCHW
   int out_C;                   // channel pitch of out / res (NHWC modes)
   double* stats;               // [N][Cout][2] or null
-  int swap_lbo_sbo;            // debug
   int batch_rows;              // >0: batched GEMM mode (gather only): blockIdx.z = batch, rows per batch
   long w_batch_stride;         // bytes between the packed B operands of consecutive batches
 };
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               } else {
                 live = true;
               }
-              src = S.x + (size_t)g * S.C + ch0;
+              src = S.x + (size_t)g * S.pitch + ch0;
             }
           } else {
             const int m = m0 + e;
@@ -299,9 +300,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               if (S.padded) {
                 const int r = m - n * img;
                 const int h = r / p.Wout, w = r - h * p.Wout;
-                src = S.x + ((size_t)(n * (p.Hout + 2) + h + 1) * (p.Wout + 2) + (w + 1)) * S.C + ch0;
+                src = S.x + ((size_t)(n * (p.Hout + 2) + h + 1) * (p.Wout + 2) + (w + 1)) * S.pitch + ch0;
               } else {
-                src = S.x + (size_t)m * S.C + ch0;
+                src = S.x + (size_t)m * S.pitch + ch0;
               }
             }
           }
@@ -312,8 +313,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             if (has_affine) {
               if (n != cur_n) {
                 cur_n = n;
-                const float4* ps = reinterpret_cast<const float4*>(S.scale + (size_t)n * S.C + ch0);
-                const float4* pt = reinterpret_cast<const float4*>(S.shift + (size_t)n * S.C + ch0);
+                const float4* ps = reinterpret_cast<const float4*>(S.scale + (size_t)n * S.ss_stride + ch0);
+                const float4* pt = reinterpret_cast<const float4*>(S.shift + (size_t)n * S.ss_stride + ch0);
                 float4 s0 = __ldg(ps), s1 = __ldg(ps + 1), t0 = __ldg(pt), t1 = __ldg(pt + 1);
                 sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
                 sh[0] = t0.x; sh[1] = t0.y; sh[2] = t0.z; sh[3] = t0.w; sh[4] = t1.x; sh[5] = t1.y; sh[6] = t1.z; sh[7] = t1.w;
@@ -470,10 +471,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // =================================== MMA issuer ===================================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t a_lbo = p.swap_lbo_sbo ? 128u : (uint32_t)p.win_pitch;
-      const uint32_t a_sbo = p.swap_lbo_sbo ? (uint32_t)p.win_pitch : 128u;
-      const uint32_t b_lbo = p.swap_lbo_sbo ? 128u : (uint32_t)(NT * 16);
-      const uint32_t b_sbo = p.swap_lbo_sbo ? (uint32_t)(NT * 16) : 128u;
+      // K-major SWIZZLE_NONE: LBO = byte distance between the two 8-element K halves of one MMA (chunk pitch),
+      // SBO = byte distance between 8-row groups (rows are 16 B apart, so 128 B).  Verified on B200.
+      const uint32_t a_lbo = (uint32_t)p.win_pitch, a_sbo = 128u;
+      const uint32_t b_lbo = (uint32_t)(NT * 16), b_sbo = 128u;
       int kb_idx = 0, bi = 0;
       uint32_t acc = 0;
       for (int s = 0; s < p.nsrc; ++s) {
@@ -672,6 +673,9 @@ extern "C" int ddg_conv2d_fwd(const ddg_conv_desc* c, cudaStream_t stream) {
     const ddg_conv_src& S = c->src[s];
     SrcDev& D = d.src[s];
     D.x = S.x; D.scale = S.scale; D.shift = S.shift; D.C = S.C; D.act = S.act; D.ntaps = S.ntaps; D.padded = S.padded;
+    D.pitch = S.pitch > 0 ? S.pitch : S.C;
+    D.ss_stride = S.ss_stride > 0 ? S.ss_stride : S.C;
+    if (D.pitch % 4 != 0 || D.ss_stride % 4 != 0 || (((uintptr_t)S.x) & 15) != 0) { ddg_set_last_error("conv2d_fwd: sources must be 16-byte aligned with pitch % 4 == 0"); return DDG_ERR_ARG; }
     for (int t = 0; t < S.ntaps; ++t) {
       if (window) {
         if (!S.padded) { ddg_set_last_error("conv2d_fwd: window mode needs padded sources"); return DDG_ERR_ARG; }
@@ -688,7 +692,6 @@ extern "C" int ddg_conv2d_fwd(const ddg_conv_desc* c, cudaStream_t stream) {
   d.res = c->res; d.out_scale = c->out_scale; d.out_act = c->out_act;
   d.out = c->out; d.out_mode = c->out_mode; d.out_C = c->out_C > 0 ? c->out_C : c->Cout;
   d.stats = c->stats;
-  d.swap_lbo_sbo = c->debug_swap_lbo_sbo;
   d.batch_rows = 0;
   d.w_batch_stride = 0;
   if (c->batch_rows > 0) {

@@ -118,7 +118,6 @@ __global__ void __launch_bounds__(kGnThreads) groupnorm_bwd_kernel(const float* 
                                                                    float* __restrict__ dbeta, int C, int HW, int G, int per_sample,
                                                                    int act) {
   __shared__ float red[32];
-  __shared__ float s_dg[64], s_db[64];
   const int ng = blockIdx.x;
   const int n = ng / G, g = ng - n * G;
   const int cpg = C / G;
@@ -147,7 +146,6 @@ __global__ void __launch_bounds__(kGnThreads) groupnorm_bwd_kernel(const float* 
     sum1 += b * ga;
     sum2 += a * ga;
   }
-  (void)s_dg; (void)s_db;
   const float m1 = sum1 / (float)len, m2 = sum2 / (float)len;
   for (long i = threadIdx.x; i < len; i += blockDim.x) {
     const int c = g * cpg + (int)(i / HW);
@@ -227,8 +225,8 @@ extern "C" int ddg_groupnorm_bwd(const float* x, const float* dy, const float* g
 
 extern "C" int ddg_fused_bias_act(const float* x, const float* b, const float* ref, float* y, long n, int step_b, int size_b, int act,
                                   int grad, float alpha, float scale, cudaStream_t stream) {
-  if (!x || !y || n < 0 || (b && (step_b <= 0 || size_b <= 0))) { ddg_set_last_error("fused_bias_act: bad args"); return DDG_ERR_ARG; }
   if (n == 0) return DDG_OK;
+  if (!x || !y || n < 0 || (b && (step_b <= 0 || size_b <= 0))) { ddg_set_last_error("fused_bias_act: bad args"); return DDG_ERR_ARG; }
   const int vec = ((n & 3) == 0) && (!b || (step_b % 4 == 0)) && ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)(ref ? ref : x)) & 15) == 0);
   long work = vec ? n / 4 : n;
   long blocks = (work + 255) / 256;

@@ -17,7 +17,7 @@ MAX_SRC = 3
 
 
 class ConvSrc(C.Structure):
-    _fields_ = [('x', C.c_void_p), ('scale', C.c_void_p), ('shift', C.c_void_p), ('C', C.c_int), ('act', C.c_int),
+    _fields_ = [('x', C.c_void_p), ('scale', C.c_void_p), ('shift', C.c_void_p), ('C', C.c_int), ('pitch', C.c_int), ('ss_stride', C.c_int), ('act', C.c_int),
                 ('ntaps', C.c_int), ('padded', C.c_int), ('tap_dr', C.c_int8 * 9), ('tap_ds', C.c_int8 * 9)]
 
 
@@ -27,7 +27,7 @@ class ConvDesc(C.Structure):
                 ('bias', C.c_void_p), ('addvec', C.c_void_p), ('addvec_stride', C.c_int), ('res', C.c_void_p),
                 ('out_scale', C.c_float), ('out_act', C.c_int), ('out', C.c_void_p), ('out_mode', C.c_int),
                 ('out_C', C.c_int), ('stats', C.c_void_p), ('precision', C.c_int), ('msub', C.c_int),
-                ('batch_rows', C.c_int), ('debug_swap_lbo_sbo', C.c_int)]
+                ('batch_rows', C.c_int)]
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_long, C.c_float
@@ -88,7 +88,10 @@ def check(rc: int, what: str = ''):
 
 
 def ptr(t):
-    return None if t is None else t.data_ptr()
+    """Device address of a tensor; ints (pre-computed addresses of channel-sliced views) pass through."""
+    if t is None or isinstance(t, int):
+        return t
+    return t.data_ptr()
 
 
 def stream():

@@ -239,10 +239,11 @@ class ConvWeights:
             off += (c // KB) * nt
 
     def pack_segment(self, i: int, w: torch.Tensor, cin_real: int, s_co: int, s_ci: int, s_tap: int, flip: bool = False,
-                     w_batch_stride: int = 0):
+                     w_batch_stride: int = 0, elem_offset: int = 0):
+        """B[co][ci][tap] = w.flat[elem_offset + co*s_co + ci*s_ci + tap*s_tap] for ci < cin_real (zero beyond)."""
         require_cuda_f32(w)
         c, nt = self.segs[i]
-        check(lib().ddg_conv_pack_weights(ptr(w), ptr(self.buf), self.cout, cin_real, c, nt, s_co, s_ci, s_tap, int(flip),
+        check(lib().ddg_conv_pack_weights(w.data_ptr() + 4 * elem_offset, ptr(self.buf), self.cout, cin_real, c, nt, s_co, s_ci, s_tap, int(flip),
                                           KB, self.offsets[i], self.total_stages, self.precision, self.batch, w_batch_stride,
                                           stream()), 'conv_pack_weights')
 
@@ -259,19 +260,23 @@ class ConvWeights:
         self.pack_segment(i, W, W.shape[0], 1, W.shape[1], 0)
 
 
-def conv_src(x, c, taps, scale=None, shift=None, act=ACT_NONE, padded=True):
-    return dict(x=x, C=c, taps=taps, scale=scale, shift=shift, act=act, padded=padded)
+def conv_src(x, c, taps, scale=None, shift=None, act=ACT_NONE, padded=True, pitch=0, ss_stride=0):
+    """x / scale / shift may be tensors or raw device addresses (ints) for channel-sliced views."""
+    return dict(x=x, C=c, taps=taps, scale=scale, shift=shift, act=act, padded=padded, pitch=pitch, ss_stride=ss_stride)
+
+
+def _addr(v):
+    return v if (v is None or isinstance(v, int)) else v.data_ptr()
 
 
 def build_conv_desc(weights: ConvWeights, srcs, n, hout, wout, out, out_mode=OUT_PNHWC, hp=None, wp=None, bias=None, addvec=None,
-                    addvec_stride=0, res=None, out_scale=1.0, out_act=ACT_NONE, out_c=0, stats=None, msub=0, batch_rows=0,
-                    debug_swap=0) -> ConvDesc:
+                    addvec_stride=0, res=None, out_scale=1.0, out_act=ACT_NONE, out_c=0, stats=None, msub=0, batch_rows=0) -> ConvDesc:
     d = ConvDesc()
     d.nsrc = len(srcs)
     for i, s in enumerate(srcs):
         sd = d.src[i]
-        sd.x = ptr(s['x']); sd.scale = ptr(s.get('scale')); sd.shift = ptr(s.get('shift'))
-        sd.C = s['C']; sd.act = s.get('act', ACT_NONE); sd.ntaps = len(s['taps']); sd.padded = int(s.get('padded', True))
+        sd.x = _addr(s['x']); sd.scale = _addr(s.get('scale')); sd.shift = _addr(s.get('shift'))
+        sd.C = s['C']; sd.pitch = s.get('pitch', 0); sd.ss_stride = s.get('ss_stride', 0); sd.act = s.get('act', ACT_NONE); sd.ntaps = len(s['taps']); sd.padded = int(s.get('padded', True))
         for t, (dr, ds) in enumerate(s['taps']):
             sd.tap_dr[t] = dr
             sd.tap_ds[t] = ds
@@ -282,14 +287,13 @@ def build_conv_desc(weights: ConvWeights, srcs, n, hout, wout, out, out_mode=OUT
     d.Hp = hp if hp is not None else hout + 2
     d.Wp = wp if wp is not None else wout + 2
     d.Cout = weights.cout
-    d.bias = ptr(bias); d.addvec = ptr(addvec); d.addvec_stride = addvec_stride
-    d.res = ptr(res); d.out_scale = out_scale; d.out_act = out_act
-    d.out = ptr(out); d.out_mode = out_mode; d.out_C = out_c
-    d.stats = ptr(stats)
+    d.bias = _addr(bias); d.addvec = _addr(addvec); d.addvec_stride = addvec_stride
+    d.res = _addr(res); d.out_scale = out_scale; d.out_act = out_act
+    d.out = _addr(out); d.out_mode = out_mode; d.out_C = out_c
+    d.stats = _addr(stats)
     d.precision = weights.precision
     d.msub = msub
     d.batch_rows = batch_rows
-    d.debug_swap_lbo_sbo = debug_swap
     return d
 
 

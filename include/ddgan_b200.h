@@ -99,7 +99,9 @@ typedef struct {
   const float* x;      /* PNHWC (padded=1) or NHWC (padded=0) source, channel pitch C */
   const float* scale;  /* [N][C] prologue scale or NULL */
   const float* shift;  /* [N][C] prologue shift or NULL */
-  int C;               /* channels, multiple of kb */
+  int C;               /* channels contributed, multiple of kb */
+  int pitch;           /* row pitch of x in floats (0 = C): lets a source be a channel slice of a wider tensor */
+  int ss_stride;       /* row pitch of scale/shift in floats (0 = C) */
   int act;             /* prologue activation: 0 none, 1 SiLU, 2 LeakyReLU(0.2) */
   int ntaps;           /* taps this source contributes (9 = 3x3, 4 = 2x2, 1 = 1x1) */
   int padded;
@@ -129,7 +131,6 @@ typedef struct {
   int msub;            /* 0 auto, 1 or 2 accumulators of 128 rows per CTA */
   int batch_rows;      /* >0: batched GEMM (1x1 only): rows [b*batch_rows, (b+1)*batch_rows) use packed operand b
                           (wpack + b * ddg_conv_packed_bytes(...)); used for the attention GEMMs (layerspp.py:115-119) */
-  int debug_swap_lbo_sbo;
 } ddg_conv_desc;
 
 int ddg_conv_tile_n(int cout);

@@ -1,0 +1,144 @@
+"""End-to-end GPU parity of the fused engines against the CPU oracle with re-randomised weights
+(random init is numerically degenerate: SURVEY.md 'five things' #5).  FP32 mode gate: 1e-4 relative L2."""
+import pytest
+import torch
+
+from oracle import ddgan_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+TOL = 1e-4
+
+
+def seeded(shape, seed, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+def _gen_case(cfg, B, seed, capture=False, precision=3):
+    from ddgan_b200.engine import GeneratorEngine
+    sd = O.randomize_params(O.ncsnpp_param_shapes(cfg), seed=seed)
+    x = seeded((B, cfg.num_channels, cfg.image_size, cfg.image_size), seed + 1)
+    z = seeded((B, cfg.nz), seed + 2)
+    t = torch.arange(B) % cfg.num_timesteps
+    with torch.no_grad():
+        ref = O.ncsnpp_forward(sd, cfg, x, t, z)
+    eng = GeneratorEngine(cfg, B, DEV, precision=precision)
+    eng.load_state_dict(sd)
+    if capture:
+        eng.capture()
+    y = eng.forward(x.to(DEV), t.to(DEV), z.to(DEV)).clone()
+    y2 = eng.forward(x.to(DEV), t.to(DEV), z.to(DEV)).clone()  # re-entrancy: stats arena is re-zeroed each call
+    assert O.rel_l2(y2.cpu(), y.cpu()) < 1e-6
+    return O.rel_l2(y.cpu(), ref), eng
+
+
+def test_arch_matches_reference_state_dict(golden):
+    from ddgan_b200 import arch
+    assert dict(arch.ncsnpp_param_shapes(arch.normalize_config(O.cifar10_config()))) == golden['ncsnpp_cifar_shapes']
+    assert list(arch.ncsnpp_param_shapes(arch.normalize_config(O.cifar10_config()))) == list(golden['ncsnpp_cifar_shapes'])
+    assert dict(arch.ncsnpp_param_shapes(arch.normalize_config(O.tiny_config()))) == golden['ncsnpp_tiny_shapes']
+    assert dict(arch.discriminator_param_shapes(6, 64, 256)) == golden['dsmall_cifar_shapes']
+    assert dict(arch.discriminator_param_shapes(6, 8, 32, large=True)) == golden['dlarge_shapes']
+
+
+def test_generator_tiny_vs_oracle_and_golden(golden):
+    cfg = O.tiny_config()
+    err, eng = _gen_case(cfg, 3, 7)
+    assert err < TOL, err
+    # the committed golden vector (reference's own output for seed 7, t = [0,3,1])
+    sd = O.randomize_params(O.ncsnpp_param_shapes(cfg), seed=7)
+    eng.load_state_dict(sd)
+    x = seeded((3, 3, 16, 16), 200); z = seeded((3, cfg.nz), 201); t = torch.tensor([0, 3, 1])
+    y = eng.forward(x.to(DEV), t.to(DEV), z.to(DEV))
+    assert O.rel_l2(y.cpu(), golden['ncsnpp_tiny_out']) < TOL
+
+
+def test_generator_cifar_vs_oracle(golden):
+    err, eng = _gen_case(O.cifar10_config(), 4, 11, capture=True)
+    assert err < TOL, err
+    # reference golden (B=2 rows of a B=4 engine: samples are independent in eval)
+    sd = O.randomize_params(O.ncsnpp_param_shapes(O.cifar10_config()), seed=8)
+    eng.load_state_dict(sd)
+    x = seeded((2, 3, 32, 32), 210); z = seeded((2, 100), 211); t = torch.tensor([3, 0])
+    y = eng.forward(torch.cat([x, x]).to(DEV), torch.cat([t, t]).to(DEV), torch.cat([z, z]).to(DEV))
+    assert O.rel_l2(y[:2].cpu(), golden['ncsnpp_cifar_out']) < TOL
+    assert O.rel_l2(y[2:].cpu(), golden['ncsnpp_cifar_out']) < TOL
+
+
+def test_generator_bf16_mode():
+    # BF16 mode: stated tolerance 2e-2 relative L2 per generator forward (bf16 operands, fp32 accumulate).
+    err, _ = _gen_case(O.tiny_config(), 3, 7, precision=1)
+    assert 1e-5 < err < 2e-2, err
+
+
+def test_discriminator_small_vs_oracle(golden):
+    from ddgan_b200.engine import DiscriminatorEngine
+    sd = O.randomize_params(O.discriminator_param_shapes(6, 16, 32), seed=9)
+    x = seeded((4, 3, 32, 32), 220); xt = seeded((4, 3, 32, 32), 221); t = torch.tensor([0, 1, 2, 3])
+    eng = DiscriminatorEngine(6, 16, 32, 32, 4, large=False, device=DEV)
+    eng.load_state_dict(sd)
+    y = eng.forward(x.to(DEV), t.to(DEV), xt.to(DEV))
+    assert O.rel_l2(y.cpu(), golden['dsmall_out']) < TOL
+    # batch 8: two stddev sets of 4 (sample i grouped with i+2, i+4, i+6)
+    x = seeded((8, 3, 32, 32), 222); xt = seeded((8, 3, 32, 32), 223); t = torch.arange(8) % 4
+    ref = O.discriminator_forward(sd, x, t, xt, 32)
+    eng = DiscriminatorEngine(6, 16, 32, 32, 8, large=False, device=DEV)
+    eng.load_state_dict(sd)
+    eng.capture()
+    y = eng.forward(x.to(DEV), t.to(DEV), xt.to(DEV))
+    assert O.rel_l2(y.cpu(), ref) < TOL
+
+
+@pytest.mark.xfail(reason='256-px maps need the segmented-window tiling (smem budget); scheduled with the HQ256 configs', strict=False)
+def test_discriminator_large_vs_golden(golden):
+    from ddgan_b200.engine import DiscriminatorEngine
+    sd = O.randomize_params(O.discriminator_param_shapes(6, 8, 32, large=True), seed=10)
+    # ngf = 8 gives 16-channel maps; the engine needs 2*ngf % 32 == 0, so check ngf = 16 against the oracle instead
+    sd = O.randomize_params(O.discriminator_param_shapes(6, 16, 32, large=True), seed=10)
+    x = seeded((4, 3, 256, 256), 230); xt = seeded((4, 3, 256, 256), 231); t = torch.tensor([0, 1, 2, 3])
+    ref = O.discriminator_forward(sd, x, t, xt, 32, large=True)
+    eng = DiscriminatorEngine(6, 16, 32, 256, 4, large=True, device=DEV)
+    eng.load_state_dict(sd)
+    y = eng.forward(x.to(DEV), t.to(DEV), xt.to(DEV))
+    assert O.rel_l2(y.cpu(), ref) < TOL
+
+
+def test_sampler_vs_oracle(golden):
+    from ddgan_b200.engine import GeneratorEngine
+    from ddgan_b200 import diffusion
+    cfg = O.tiny_config()
+    sd = O.randomize_params(O.ncsnpp_param_shapes(cfg), seed=7)
+    B = 3
+    eng = GeneratorEngine(cfg, B, DEV)
+    eng.load_state_dict(sd)
+    # oracle with recorded noise (reference draw order: z, then posterior noise, per step)
+    draws = []
+    g = torch.Generator().manual_seed(5)
+
+    def noise_fn(shape):
+        d = torch.randn(*shape, generator=g)
+        draws.append(d)
+        return d
+    x_init = seeded((B, 3, 16, 16), 77)
+    pc = O.posterior_coefficients(cfg)
+    ref = O.sample_from_model(pc, lambda x, t, z: O.ncsnpp_forward(sd, cfg, x, t, z), 4, x_init, cfg.nz, noise_fn)
+    # (1) functional API, same signature as test_ddgan.sample_from_model
+    it = iter(draws)
+    pcd = diffusion.PosteriorCoefficients(cfg, DEV)
+    y = diffusion.sample_from_model(pcd, eng.forward, 4, x_init.to(DEV), None, cfg, noise_fn=lambda shape: next(it).to(DEV))
+    assert O.rel_l2(y.cpu(), ref) < TOL
+    # (2) whole loop as one CUDA graph with injected noise
+    smp = diffusion.GraphSampler(eng, cfg)
+    smp.capture()
+    for k in range(4):
+        smp.z_noise[k].copy_(draws[2 * k]); smp.p_noise[k].copy_(draws[2 * k + 1])
+    y = smp.sample(x_init.to(DEV), fresh_noise=False)
+    assert O.rel_l2(y.cpu(), ref) < TOL
+    # the committed golden (torch.manual_seed(1024) CPU stream of the reference run)
+    torch.manual_seed(1024)
+    x_init = torch.randn(B, 3, 16, 16)
+    d2 = [torch.randn(*s) for _ in range(4) for s in ((B, cfg.nz), (B, 3, 16, 16))]
+    for k in range(4):
+        smp.z_noise[k].copy_(d2[2 * k]); smp.p_noise[k].copy_(d2[2 * k + 1])
+    y = smp.sample(x_init.to(DEV), fresh_noise=False)
+    assert O.rel_l2(y.cpu(), golden['sample_tiny']) < TOL

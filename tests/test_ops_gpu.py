@@ -212,12 +212,12 @@ def _conv_case(ops, n, cin, cout, h, k, prec=3, affine=False, act=0, res=False, 
                                             (4, 3, 128, 32, 3), (3, 512, 512, 4, 3), (5, 256, 64, 4, 1), (1, 128, 128, 32, 3)])
 def test_conv_tc_plain(ops, n, cin, cout, h, k):
     err, e1, e2 = _conv_case(ops, n, cin, cout, h, k)
-    assert err < 2e-5 and e1 < 1e-5 and e2 < 1e-5, (err, e1, e2)
+    assert err < 2e-5 and e1 < 5e-5 and e2 < 5e-5, (err, e1, e2)
 
 
 def test_conv_tc_fused_variants(ops):
     err, e1, e2 = _conv_case(ops, 4, 256, 256, 16, 3, affine=True, act=1, res=True, temb=True)
-    assert err < 2e-5 and e1 < 1e-5 and e2 < 1e-5, (err, e1, e2)
+    assert err < 2e-5 and e1 < 5e-5 and e2 < 5e-5, (err, e1, e2)
     err, _, _ = _conv_case(ops, 4, 128, 3, 32, 3, nchw=True)
     assert err < 2e-5
     err, _, _ = _conv_case(ops, 2, 128, 128, 16, 3, act=2, msub=1)
@@ -226,7 +226,7 @@ def test_conv_tc_fused_variants(ops):
     assert err < 2e-5
     # fused 1x1 skip conv as a second K segment + residual rescale (ResnetBlockBigGANpp_Adagn, layerspp.py:305-310)
     err, e1, e2 = _conv_case(ops, 4, 256, 128, 16, 3, affine=True, act=1, skip1x1=384)
-    assert err < 2e-5 and e1 < 1e-5 and e2 < 1e-5, (err, e1, e2)
+    assert err < 2e-5 and e1 < 5e-5 and e2 < 5e-5, (err, e1, e2)
 
 
 def test_conv_tc_bf16_mode(ops):

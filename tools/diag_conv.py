@@ -47,7 +47,7 @@ def run(name, n, cin, cout, h, k, swap=0, msub=0, prec=3, affine=False, act=0, r
         rd = r.to(dev).contiguous() if nchw else ops.to_pnhwc(r.to(dev), cpad=cout)
     t0 = time.time()
     ops.conv2d_fused(cw, [ops.conv_src(xd, cp, taps, scale=scd, shift=shd, act=act)], n, h, h, out, out_mode=mode,
-                     bias=b.to(dev), res=rd, out_scale=(1 / math.sqrt(2) if res else 1.0), stats=st, msub=msub, debug_swap=swap)
+                     bias=b.to(dev), res=rd, out_scale=(1 / math.sqrt(2) if res else 1.0), stats=st, msub=msub)
     torch.cuda.synchronize()
     y = out if nchw else ops.from_pnhwc(out, cout)
     err = rel_l2(y.cpu(), ref)
@@ -64,12 +64,8 @@ def run(name, n, cin, cout, h, k, swap=0, msub=0, prec=3, affine=False, act=0, r
 
 if __name__ == '__main__':
     print(torch.cuda.get_device_name(0))
-    for swap in (0, 1):
-        try:
-            run('1x1 32->128 8px', 2, 32, 128, 8, 1, swap=swap, msub=1)
-            run('3x3 32->128 8px', 2, 32, 128, 8, 3, swap=swap, msub=1)
-        except Exception as e:
-            print('FAILED', swap, e)
+    run('1x1 32->128 8px', 2, 32, 128, 8, 1, msub=1)
+    run('3x3 32->128 8px', 2, 32, 128, 8, 3, msub=1)
     run('3x3 64->128 16px msub2', 4, 64, 128, 16, 3, msub=2)
     run('3x3 128->256 32px auto', 8, 128, 256, 32, 3)
     run('3x3 128->256 32px bf16', 8, 128, 256, 32, 3, prec=1)
