@@ -161,6 +161,7 @@ struct ConvDev {
   int out_mode;                // 0 padded NHWC, 1 NHWC, 2 NCHW
   int out_C;                   // channel pitch of out / res (NHWC modes)
   double* stats;               // [N][Cout][2] or null
+  long long* prof;             // optional: per-role cycle counters of CTA (0,0) (bring-up / tuning aid)
   int batch_rows;              // >0: batched GEMM mode (gather only): blockIdx.z = batch, rows per batch
   long w_batch_stride;         // bytes between the packed B operands of consecutive batches
 };
@@ -249,105 +250,184 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   if (warp < kProdWarps) {
     // =================================== A producers ===================================
+    // Software-pipelined: each thread owns one 16-byte channel chunk (c) and up to IMAX window rows (e0 + k*ESTEP).
+    // Row geometry (global offset, sample index, liveness) is computed once per source; the rows of K-block i+1 are
+    // prefetched into registers while K-block i is converted and stored, so one global-load latency is exposed per
+    // K-block at most (it was one per row before: the dominant long-scoreboard stall in the first ncu capture).
     const int tid = threadIdx.x;                     // 0..255
     constexpr int NPT = kProdWarps * 32;
+    constexpr int ESTEP = NPT / KCH;
+    constexpr int IMAX = (MSUB == 2) ? 5 : 4;   // 320 threads cap ptxas at 168 registers: a 6th pipelined row would spill
     const int c = tid % KCH;                         // fixed 16-byte chunk of this thread
     const int e0 = tid / KCH;
-    constexpr int ESTEP = NPT / KCH;
-    int kb_idx = 0;
-    for (int s = 0; s < p.nsrc; ++s) {
-      const SrcDev& S = p.src[s];
-      const bool has_affine = (S.scale != nullptr);
-      // rows of the window actually needed by this source
-      int row_lo = 0, row_hi = p.win_rows;
-      if (p.window && S.ntaps == 1) { row_lo = S.tapoff[0]; row_hi = S.tapoff[0] + MT; }
-      for (int kb = 0; kb < S.C / KB; ++kb, ++kb_idx) {
-        const int st = kb_idx & 1;
-        const uint32_t ph = (kb_idx >> 1) & 1;
-        mbar_wait(emptyA(st), ph ^ 1);
-        uint8_t* dst_hi = sA + st * a_stage + c * p.win_pitch;
-        uint8_t* dst_lo = dst_hi + a_plane;
-        const int ch0 = kb * KB + c * 8;
-        int cur_n = -1;
-        float sc[8], sh[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; }
-        for (int e = row_lo + e0; e < row_hi; e += ESTEP) {
-          float v[8];
-          bool live = false;
-          int n = 0;
-          const float* src = nullptr;
-          if (p.window) {
-            const int g = m0 - p.margin + e;         // row in padded linear space
-            if (g >= 0 && g < p.Mtotal) {
-              const int img = p.Hp * p.Wp;
-              n = g / img;
-              if (has_affine) {                      // padding must stay zero after the affine prologue
-                const int r = g - n * img;
-                const int hp = r / p.Wp, wp = r - hp * p.Wp;
-                live = (hp >= 1) && (hp < p.Hp - 1) && (wp >= 1) && (wp < p.Wp - 1);
-              } else {
-                live = true;
-              }
-              src = S.x + (size_t)g * S.pitch + ch0;
-            }
-          } else {
-            const int m = m0 + e;
-            if (m < m_end) {
-              live = true;
-              const int img = p.Hout * p.Wout;
-              n = m / img;
-              if (S.padded) {
-                const int r = m - n * img;
-                const int h = r / p.Wout, w = r - h * p.Wout;
-                src = S.x + ((size_t)(n * (p.Hout + 2) + h + 1) * (p.Wout + 2) + (w + 1)) * S.pitch + ch0;
-              } else {
-                src = S.x + (size_t)m * S.pitch + ch0;
-              }
-            }
+
+    // off >= 0: element offset of the row in the source; -1: store zeros; -2: row not part of this source's window
+    auto row_info = [&](const SrcDev& S, int e, int row_hi, int& off, int& nn) {
+      off = -2; nn = 0;
+      if (e >= row_hi) return;
+      off = -1;
+      if (p.window) {
+        const int g = m0 - p.margin + e;             // row in padded linear space
+        if (g >= 0 && g < p.Mtotal) {
+          const int img = p.Hp * p.Wp;
+          const int n = g / img;
+          bool live = true;
+          if (S.scale != nullptr) {                  // padding must stay zero after the affine prologue
+            const int r = g - n * img;
+            const int hp = r / p.Wp, wp = r - hp * p.Wp;
+            live = (hp >= 1) && (hp < p.Hp - 1) && (wp >= 1) && (wp < p.Wp - 1);
           }
-          if (live) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(src));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-            if (has_affine) {
-              if (n != cur_n) {
-                cur_n = n;
-                const float4* ps = reinterpret_cast<const float4*>(S.scale + (size_t)n * S.ss_stride + ch0);
-                const float4* pt = reinterpret_cast<const float4*>(S.shift + (size_t)n * S.ss_stride + ch0);
-                float4 s0 = __ldg(ps), s1 = __ldg(ps + 1), t0 = __ldg(pt), t1 = __ldg(pt + 1);
-                sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
-                sh[0] = t0.x; sh[1] = t0.y; sh[2] = t0.z; sh[3] = t0.w; sh[4] = t1.x; sh[5] = t1.y; sh[6] = t1.z; sh[7] = t1.w;
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
-            }
-            if (S.act == ACT_SILU) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
-            } else if (S.act == ACT_LEAKY) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = leaky_f(v[j]);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = 0.f;
-          }
-          uint4 hi, lo;
-          split_bf16x2(v[0], v[1], hi.x, lo.x);
-          split_bf16x2(v[2], v[3], hi.y, lo.y);
-          split_bf16x2(v[4], v[5], hi.z, lo.z);
-          split_bf16x2(v[6], v[7], hi.w, lo.w);
-          *reinterpret_cast<uint4*>(dst_hi + e * 16) = hi;
-          if (NPL == 2) *reinterpret_cast<uint4*>(dst_lo + e * 16) = lo;
+          if (live) { off = g * S.pitch; nn = n; }
         }
-        fence_proxy_async();
-        mbar_arrive(fullA(st));
+      } else {
+        const int m = m0 + e;
+        if (m < m_end) {
+          const int img = p.Hout * p.Wout;
+          const int n = m / img;
+          nn = n;
+          if (S.padded) {
+            const int r = m - n * img;
+            const int h = r / p.Wout, w = r - h * p.Wout;
+            off = ((n * (p.Hout + 2) + h + 1) * (p.Wout + 2) + (w + 1)) * S.pitch;
+          } else {
+            off = m * S.pitch;
+          }
+        }
+      }
+    };
+    auto src_rows = [&](const SrcDev& S, int& row_lo, int& row_hi) {
+      row_lo = 0; row_hi = p.win_rows;
+      if (p.window && S.ntaps == 1) { row_lo = S.tapoff[0]; row_hi = S.tapoff[0] + MT; }
+    };
+    auto transform_store = [&](const SrcDev& S, float* v, bool live, int n, int ch0, int& cur_n, float* sc, float* sh,
+                               uint8_t* dst_hi, uint8_t* dst_lo, int e) {
+      if (live) {
+        if (S.scale != nullptr) {
+          if (n != cur_n) {
+            cur_n = n;
+            const float4* ps = reinterpret_cast<const float4*>(S.scale + (size_t)n * S.ss_stride + ch0);
+            const float4* pt = reinterpret_cast<const float4*>(S.shift + (size_t)n * S.ss_stride + ch0);
+            const float4 s0 = __ldg(ps), s1 = __ldg(ps + 1), t0 = __ldg(pt), t1 = __ldg(pt + 1);
+            sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+            sh[0] = t0.x; sh[1] = t0.y; sh[2] = t0.z; sh[3] = t0.w; sh[4] = t1.x; sh[5] = t1.y; sh[6] = t1.z; sh[7] = t1.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+        }
+        if (S.act == ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+        } else if (S.act == ACT_LEAKY) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = leaky_f(v[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      }
+      uint4 hi, lo;
+      split_bf16x2(v[0], v[1], hi.x, lo.x);
+      split_bf16x2(v[2], v[3], hi.y, lo.y);
+      split_bf16x2(v[4], v[5], hi.z, lo.z);
+      split_bf16x2(v[6], v[7], hi.w, lo.w);
+      *reinterpret_cast<uint4*>(dst_hi + e * 16) = hi;
+      if (NPL == 2) *reinterpret_cast<uint4*>(dst_lo + e * 16) = lo;
+    };
+
+    const bool prof_on = (p.prof != nullptr) && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0;
+    long long t_prod0 = clock64(), w_emptyA = 0;
+    float cur[IMAX][8], nxt[IMAX][8];
+    int off_c[IMAX], nn_c[IMAX], off_n[IMAX], nn_n[IMAX];
+    int s_cur = 0, kb_cur = 0;
+    {
+      int lo_, hi_;
+      src_rows(p.src[0], lo_, hi_);
+#pragma unroll
+      for (int k = 0; k < IMAX; ++k) {
+        row_info(p.src[0], lo_ + e0 + k * ESTEP, hi_, off_c[k], nn_c[k]);
+        if (off_c[k] >= 0) {
+          const float4* q = reinterpret_cast<const float4*>(p.src[0].x + off_c[k] + c * 8);
+          const float4 a = __ldg(q), b = __ldg(q + 1);
+          cur[k][0] = a.x; cur[k][1] = a.y; cur[k][2] = a.z; cur[k][3] = a.w;
+          cur[k][4] = b.x; cur[k][5] = b.y; cur[k][6] = b.z; cur[k][7] = b.w;
+        }
+      }
+    }
+    for (int kb_idx = 0; kb_idx < nkb_total; ++kb_idx) {
+      const SrcDev& S = p.src[s_cur];
+      // ---- prefetch the next K-block ----
+      int s_nxt = s_cur, kb_nxt = kb_cur + 1;
+      if (kb_nxt >= S.C / KB) { s_nxt = s_cur + 1; kb_nxt = 0; }
+      const bool has_next = kb_idx + 1 < nkb_total;
+      if (has_next) {
+        const SrcDev& Sn = p.src[s_nxt];
+        if (s_nxt != s_cur) {
+          int lo_, hi_;
+          src_rows(Sn, lo_, hi_);
+#pragma unroll
+          for (int k = 0; k < IMAX; ++k) row_info(Sn, lo_ + e0 + k * ESTEP, hi_, off_n[k], nn_n[k]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < IMAX; ++k) { off_n[k] = off_c[k]; nn_n[k] = nn_c[k]; }
+        }
+        const int chn = kb_nxt * KB + c * 8;
+#pragma unroll
+        for (int k = 0; k < IMAX; ++k) {
+          if (off_n[k] >= 0) {
+            const float4* q = reinterpret_cast<const float4*>(Sn.x + off_n[k] + chn);
+            const float4 a = __ldg(q), b = __ldg(q + 1);
+            nxt[k][0] = a.x; nxt[k][1] = a.y; nxt[k][2] = a.z; nxt[k][3] = a.w;
+            nxt[k][4] = b.x; nxt[k][5] = b.y; nxt[k][6] = b.z; nxt[k][7] = b.w;
+          }
+        }
+      }
+      // ---- convert + store the current K-block ----
+      const int st = kb_idx & 1;
+      const uint32_t ph = (kb_idx >> 1) & 1;
+      { const long long tw = clock64(); mbar_wait(emptyA(st), ph ^ 1); w_emptyA += clock64() - tw; }
+      uint8_t* dst_hi = sA + st * a_stage + c * p.win_pitch;
+      uint8_t* dst_lo = dst_hi + a_plane;
+      const int ch0 = kb_cur * KB + c * 8;
+      int cur_n = -1;
+      float sc[8], sh[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; }
+      int row_lo, row_hi;
+      src_rows(S, row_lo, row_hi);
+#pragma unroll
+      for (int k = 0; k < IMAX; ++k) {
+        if (off_c[k] != -2) transform_store(S, cur[k], off_c[k] >= 0, nn_c[k], ch0, cur_n, sc, sh, dst_hi, dst_lo, row_lo + e0 + k * ESTEP);
+      }
+      // rows beyond the register pipeline (very wide windows only)
+      for (int e = row_lo + e0 + IMAX * ESTEP; e < row_hi; e += ESTEP) {
+        int off, nn;
+        row_info(S, e, row_hi, off, nn);
+        float v[8];
+        if (off >= 0) {
+          const float4* q = reinterpret_cast<const float4*>(S.x + off + ch0);
+          const float4 a = __ldg(q), b = __ldg(q + 1);
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        }
+        transform_store(S, v, off >= 0, nn, ch0, cur_n, sc, sh, dst_hi, dst_lo, e);
+      }
+      fence_proxy_async();
+      mbar_arrive(fullA(st));
+      // ---- rotate the register pipeline ----
+      if (has_next) {
+#pragma unroll
+        for (int k = 0; k < IMAX; ++k) {
+          off_c[k] = off_n[k]; nn_c[k] = nn_n[k];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cur[k][j] = nxt[k][j];
+        }
+        s_cur = s_nxt; kb_cur = kb_nxt;
       }
     }
 
     // =================================== epilogue ===================================
+    const long long t_prod1 = clock64();
     mbar_wait(accFull, 0);
+    const long long t_epi0 = clock64();
     tc_fence_after();
     const int quad = warp & 3;                       // TMEM lane quadrant accessible by this warp
     const int half = warp >> 2;                      // column half handled by this warp
@@ -369,15 +449,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
         tmem_ld_wait();
         if (col0 < p.Cout) {
+          const bool full = (col0 + CW <= p.Cout);
+          if (full) {
+            // vectorised per-channel bias and per-(sample, channel) add (Dense_0(temb) / dense_t1)
+            if (p.bias) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-          for (int j = 0; j < CW; ++j) {
-            const int cc = col0 + j;
-            float y = v[j];
-            if (cc < p.Cout) {
-              if (p.bias) y += __ldg(p.bias + cc);
-              if (p.addvec) y += __ldg(p.addvec + (size_t)n * p.addvec_stride + cc);
+              for (int j = 0; j < CW / 4; ++j) {
+                const float4 b = __ldg(b4 + j);
+                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+              }
             }
-            v[j] = y;
+            if (p.addvec) {
+              const float4* a4 = reinterpret_cast<const float4*>(p.addvec + (size_t)n * p.addvec_stride + col0);
+#pragma unroll
+              for (int j = 0; j < CW / 4; ++j) {
+                const float4 b = __ldg(a4 + j);
+                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+              const int cc = col0 + j;
+              if (cc < p.Cout) {
+                if (p.bias) v[j] += __ldg(p.bias + cc);
+                if (p.addvec) v[j] += __ldg(p.addvec + (size_t)n * p.addvec_stride + cc);
+              }
+            }
           }
           if (valid) {
             if (p.out_mode != 2) {
@@ -389,8 +488,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                   v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
                 }
               }
+              const float osc = p.out_scale;
+              if (p.out_act == ACT_TANH) {
 #pragma unroll
-              for (int j = 0; j < CW; ++j) v[j] = apply_act(v[j] * p.out_scale, p.out_act);
+                for (int j = 0; j < CW; ++j) v[j] = tanhf(v[j] * osc);
+              } else {
+#pragma unroll
+                for (int j = 0; j < CW; ++j) v[j] *= osc;
+              }
               float4* o4 = reinterpret_cast<float4*>(p.out + obase + col0);
 #pragma unroll
               for (int j = 0; j < CW / 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -453,17 +558,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
     tc_fence_before();
+    if (prof_on && tid == 0) {
+      p.prof[0] = t_prod1 - t_prod0;   // producer loop total
+      p.prof[1] = w_emptyA;            // ... of which waiting for a free A stage
+      p.prof[2] = t_epi0 - t_prod1;    // waiting for the accumulator after the last A stage
+      p.prof[3] = clock64() - t_epi0;  // epilogue
+    }
   } else if (warp == kProdWarps) {
     // =================================== weight loader (TMA bulk) ===================================
     if (lane == 0) {
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)ntile * p.total_stages * Cfg::B_STAGE +
                             (p.batch_rows > 0 ? (size_t)blockIdx.z * p.w_batch_stride : 0);
+      long long w_emptyB = 0;
+      const long long t_l0 = clock64();
       for (int i = 0; i < p.total_stages; ++i) {
         const int st = i % NSB;
         const uint32_t ph = (i / NSB) & 1;
-        mbar_wait(emptyB(st), ph ^ 1);
+        { const long long tw = clock64(); mbar_wait(emptyB(st), ph ^ 1); w_emptyB += clock64() - tw; }
         mbar_arrive_expect_tx(fullB(st), Cfg::B_STAGE);
         tma_bulk_g2s(smem_u32(sB + st * Cfg::B_STAGE), wsrc + (size_t)i * Cfg::B_STAGE, Cfg::B_STAGE, fullB(st));
+      }
+      if (p.prof != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) {
+        p.prof[4] = clock64() - t_l0;  // loader loop total
+        p.prof[5] = w_emptyB;          // ... waiting for a free B stage
       }
     }
     __syncwarp();
@@ -477,17 +594,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t b_lbo = (uint32_t)(NT * 16), b_sbo = 128u;
       int kb_idx = 0, bi = 0;
       uint32_t acc = 0;
+      long long w_fullA = 0, w_fullB = 0;
+      const long long t_m0 = clock64();
       for (int s = 0; s < p.nsrc; ++s) {
         const SrcDev& S = p.src[s];
         for (int kb = 0; kb < S.C / KB; ++kb, ++kb_idx) {
           const int stA = kb_idx & 1;
-          mbar_wait(fullA(stA), (kb_idx >> 1) & 1);
+          { const long long tw = clock64(); mbar_wait(fullA(stA), (kb_idx >> 1) & 1); w_fullA += clock64() - tw; }
           tc_fence_after();
           const uint32_t a_hi = smem_u32(sA + stA * a_stage);
           const uint32_t a_lo = a_hi + a_plane;
           for (int t = 0; t < S.ntaps; ++t, ++bi) {
             const int stB = bi % NSB;
-            mbar_wait(fullB(stB), (bi / NSB) & 1);
+            { const long long tw = clock64(); mbar_wait(fullB(stB), (bi / NSB) & 1); w_fullB += clock64() - tw; }
             tc_fence_after();
             const uint32_t b_hi = smem_u32(sB + stB * Cfg::B_STAGE);
             const uint32_t b_lo = b_hi + Cfg::B_PLANE;
@@ -521,6 +640,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
       }
       umma_commit(accFull);
+      if (p.prof != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) {
+        p.prof[6] = clock64() - t_m0;  // MMA issue loop total
+        p.prof[7] = w_fullA;           // ... waiting for A
+        p.prof[8] = w_fullB;           // ... waiting for B
+      }
     }
     __syncwarp();
   }
@@ -694,6 +818,7 @@ extern "C" int ddg_conv2d_fwd(const ddg_conv_desc* c, cudaStream_t stream) {
   d.stats = c->stats;
   d.batch_rows = 0;
   d.w_batch_stride = 0;
+  d.prof = (long long*)c->debug_prof;
   if (c->batch_rows > 0) {
     if (window || d.Mtotal % c->batch_rows != 0) { ddg_set_last_error("conv2d_fwd: batched mode needs a 1x1 problem with Mtotal % batch_rows == 0"); return DDG_ERR_ARG; }
     d.batch_rows = c->batch_rows;

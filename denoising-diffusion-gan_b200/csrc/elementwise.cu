@@ -26,7 +26,7 @@ __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* 
 constexpr int kLinRows = 32;
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                      const float* __restrict__ b, float* __restrict__ y, int N, int K, int J,
-                                                     int ldx, int ldy, int act_in, int act_out, int pixel_norm) {
+                                                     int ldx, int ldy, int act_in, int act_out, int pixel_norm, int cpw) {
   extern __shared__ float sx[];  // [kLinRows][K]
   const int n0 = blockIdx.y * kLinRows;
   const int rows = min(kLinRows, N - n0);
@@ -43,9 +43,9 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x
     for (int k = lane; k < K; k += 32) sx[r * K + k] = apply_act(xr[k] * nrm, act_in);
   }
   __syncthreads();
-  const int jpb = 8 * 4;  // 4 columns per warp per block
-  for (int jj = 0; jj < 4; ++jj) {
-    const int j = blockIdx.x * jpb + warp * 4 + jj;
+  const int jpb = 8 * cpw;  // cpw columns per warp per block (1 for narrow layers: more CTAs)
+  for (int jj = 0; jj < cpw; ++jj) {
+    const int j = blockIdx.x * jpb + warp * cpw + jj;
     if (j >= J) break;
     const float* wr = W + (size_t)j * K;
     const float bj = b ? b[j] : 0.f;
@@ -299,8 +299,9 @@ extern "C" int ddg_linear(const float* x, const float* W, const float* b, float*
   if (smem > 200 * 1024) { ddg_set_last_error("linear: K too large"); return DDG_ERR_UNSUPPORTED; }
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-  dim3 grid((J + 31) / 32, (N + kLinRows - 1) / kLinRows);
-  linear_kernel<<<grid, 256, smem, stream>>>(x, W, b, y, N, K, J, ldx, ldy, act_in, act_out, pixel_norm);
+  const int cpw = J <= 2048 ? 1 : 4;
+  dim3 grid((J + 8 * cpw - 1) / (8 * cpw), (N + kLinRows - 1) / kLinRows);
+  linear_kernel<<<grid, 256, smem, stream>>>(x, W, b, y, N, K, J, ldx, ldy, act_in, act_out, pixel_norm, cpw);
   DDG_CHECK_LAUNCH();
   return DDG_OK;
 }
