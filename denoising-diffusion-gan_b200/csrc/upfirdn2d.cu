@@ -92,11 +92,13 @@ __device__ __forceinline__ void fma4(float4& a, const float4& v, float w) {
 // mode 1: up2 (H -> 2H), mode 2: down2 (H -> H/2), mode 3: pad(2,2) FIR H -> H+1 stored space-to-depth
 __global__ void __launch_bounds__(256) fir_pnhwc_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                                         const float* __restrict__ shift, int act, float* __restrict__ out, int N, int H,
-                                                        int W, int C, int mode, int out_pitch) {
+                                                        int W, int C, int mode, int out_pitch, float gain) {
   const float t4[4] = {1.f, 3.f, 3.f, 1.f};
   const int C4 = C / 4;
   int OH, OW;
-  if (mode == 1) { OH = 2 * H; OW = 2 * W; } else if (mode == 2) { OH = H / 2; OW = W / 2; } else { OH = H + 1; OW = W + 1; }
+  // (H, W) is always the size of the *non-s2d* image: the input for modes 1-3, the output for mode 4
+  if (mode == 1) { OH = 2 * H; OW = 2 * W; } else if (mode == 2) { OH = H / 2; OW = W / 2; } else if (mode == 3) { OH = H + 1; OW = W + 1; }
+  else { OH = H; OW = W; }
   const long total = (long)N * OH * OW * C4;
   const bool affine = scale != nullptr;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -122,7 +124,21 @@ __global__ void __launch_bounds__(256) fir_pnhwc_kernel(const float* __restrict_
           const int ix = (ox + j - 2) >> 1;
           if (ox + j - 2 < 0 || ix >= W) continue;
           const size_t off = ((size_t)(n * (H + 2) + iy + 1) * (W + 2) + (ix + 1)) * C + c4 * 4;
-          fma4(acc, load_tr(x, off, sc, sh, affine, act), t4[i] * t4[j] * (4.f / 64.f));
+          fma4(acc, load_tr(x, off, sc, sh, affine, act), t4[i] * t4[j] * (4.f / 64.f) * gain);
+        }
+      }
+    } else if (mode == 4) {
+      // adjoint of mode 3: dX[y][x] = sum_{i,j} k[i][j] * gfir[y - i + 2][x - j + 2], gfir stored space-to-depth with pitch
+      // out_pitch (= the s2d tensor's channel pitch, 4*C) in cells of (H/2 + 3) x (W/2 + 3)
+      const int Hc = H / 2 + 3, Wc = W / 2 + 3;
+      for (int i = 0; i < 4; ++i) {
+        const int fy = oy - i + 2;
+        if (fy < 0 || fy > H) continue;
+        for (int j = 0; j < 4; ++j) {
+          const int fx = ox - j + 2;
+          if (fx < 0 || fx > W) continue;
+          const size_t off = ((size_t)(n * Hc + (fy >> 1) + 1) * Wc + ((fx >> 1) + 1)) * out_pitch + (size_t)((fy & 1) * 2 + (fx & 1)) * C + c4 * 4;
+          fma4(acc, __ldg(reinterpret_cast<const float4*>(x + off)), t4[i] * t4[j] * (1.f / 64.f) * gain);
         }
       }
     } else {
@@ -135,7 +151,7 @@ __global__ void __launch_bounds__(256) fir_pnhwc_kernel(const float* __restrict_
           const int ix = ox * down + j - pad;
           if (ix < 0 || ix >= W) continue;
           const size_t off = ((size_t)(n * (H + 2) + iy + 1) * (W + 2) + (ix + 1)) * C + c4 * 4;
-          fma4(acc, load_tr(x, off, sc, sh, affine, act), t4[i] * t4[j] * (1.f / 64.f));
+          fma4(acc, load_tr(x, off, sc, sh, affine, act), t4[i] * t4[j] * (1.f / 64.f) * gain);
         }
       }
     }
@@ -144,6 +160,8 @@ __global__ void __launch_bounds__(256) fir_pnhwc_kernel(const float* __restrict_
       // space-to-depth cell (oy/2, ox/2), sub-position (oy&1, ox&1); buffer [N][Ho+3][Wo+3][out_pitch], Ho = H/2
       const int Hc = H / 2 + 3, Wc = W / 2 + 3;
       ooff = ((size_t)(n * Hc + (oy >> 1) + 1) * Wc + ((ox >> 1) + 1)) * out_pitch + (size_t)((oy & 1) * 2 + (ox & 1)) * C + c4 * 4;
+    } else if (mode == 4) {
+      ooff = ((size_t)(n * (OH + 2) + oy + 1) * (OW + 2) + (ox + 1)) * C + c4 * 4;
     } else {
       ooff = ((size_t)(n * (OH + 2) + oy + 1) * (OW + 2) + (ox + 1)) * out_pitch + c4 * 4;
     }
@@ -184,16 +202,15 @@ extern "C" int ddg_upfirdn2d(const float* x, const float* k, float* out, long pl
 }
 
 extern "C" int ddg_fir_pnhwc(const float* x, const float* scale, const float* shift, int act, float* out, int N, int H, int W, int C,
-                             int mode, int out_pitch, double* stats, cudaStream_t stream) {
-  (void)stats;
-  if (!x || !out || C % 4 != 0 || mode < 1 || mode > 3 || ((scale == nullptr) != (shift == nullptr))) { ddg_set_last_error("fir_pnhwc: bad args"); return DDG_ERR_ARG; }
-  if ((mode == 2 || mode == 3) && ((H | W) & 1)) { ddg_set_last_error("fir_pnhwc: odd size"); return DDG_ERR_UNSUPPORTED; }
-  int OH = mode == 1 ? 2 * H : (mode == 2 ? H / 2 : H + 1);
-  int OW = mode == 1 ? 2 * W : (mode == 2 ? W / 2 : W + 1);
+                             int mode, int out_pitch, float gain, cudaStream_t stream) {
+  if (!x || !out || C % 4 != 0 || mode < 1 || mode > 4 || ((scale == nullptr) != (shift == nullptr))) { ddg_set_last_error("fir_pnhwc: bad args"); return DDG_ERR_ARG; }
+  if ((mode == 2 || mode == 3 || mode == 4) && ((H | W) & 1)) { ddg_set_last_error("fir_pnhwc: odd size"); return DDG_ERR_UNSUPPORTED; }
+  int OH = mode == 1 ? 2 * H : (mode == 2 ? H / 2 : (mode == 3 ? H + 1 : H));
+  int OW = mode == 1 ? 2 * W : (mode == 2 ? W / 2 : (mode == 3 ? W + 1 : W));
   const long total = (long)N * OH * OW * (C / 4);
   long blocks = (total + 255) / 256;
   if (blocks > 148L * 32) blocks = 148L * 32;
-  fir_pnhwc_kernel<<<(int)blocks, 256, 0, stream>>>(x, scale, shift, act, out, N, H, W, C, mode, out_pitch);
+  fir_pnhwc_kernel<<<(int)blocks, 256, 0, stream>>>(x, scale, shift, act, out, N, H, W, C, mode, out_pitch, gain);
   DDG_CHECK_LAUNCH();
   return DDG_OK;
 }

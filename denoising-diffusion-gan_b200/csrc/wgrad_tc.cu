@@ -1,0 +1,305 @@
+// Weight gradient of the implicit-GEMM convolution on tcgen05 / TMEM (sm_100a).
+//
+//   dW[co][ci][tap] = sum over output positions q of  dY[q][co] * X[q + off(tap)][ci]
+//
+// (the wgrad cuDNN computes for nn.Conv2d in the reference's backward, reached from ddgan.py:459,467,477,506).
+// GEMM view per tap: D_tap[M = co][N = ci] += dY^T[M][K = pixels] * X_shifted[K][N]: the contraction runs over pixels, and in
+// NHWC the contiguous axis is the channel, so both operands are MN-major.  The shared-memory layout is the same
+// [chunk of 8 channels][row][8 x bf16] used by the forward kernel; read as an MN-major SWIZZLE_NONE operand it has
+// SBO = chunk pitch (next 8 channels) and LBO = 128 B (next 8 pixel rows), and a filter tap is again a start-address offset of
+// off(tap) rows.  dY is stored PNHWC with a zero border, so border positions contribute nothing and need no masking.
+//
+// One CTA owns a (128 output channels) x (32 input channels) x (all taps) block of dW -- 9 x 32 = 288 fp32 TMEM columns --
+// and a slice of the pixel space (split-K); it streams pixel tiles of 128 rows through a 2-stage smem ring (producer warps
+// convert fp32 -> bf16 hi/lo; BF16x3 as in the forward), accumulates in TMEM across all its tiles, and finally adds its
+// block into dW with fp32 reductions (red.global.add).
+#include "common.cuh"
+#include "ddgan_b200.h"
+
+namespace ddg {
+
+// ---- PTX wrappers (same as conv_tc.cu; kept local so each translation unit is self-contained) ----
+__device__ __forceinline__ uint32_t w_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void w_mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void w_mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void w_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void w_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void w_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t w_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void w_tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+constexpr int kWProdWarps = 8;
+constexpr int kWThreads = (kWProdWarps + 1) * 32;   // + 1 MMA warp (also owns TMEM alloc)
+constexpr int KT = 128;                              // pixel rows per stage (GEMM K per stage)
+constexpr int MCO = 128;                             // output channels per CTA (GEMM M)
+constexpr int NCI = 32;                              // input channels per CTA (GEMM N per tap)
+
+struct WgradDev {
+  const float* x;      // PNHWC source as seen by the conv, pitch xpitch
+  const float* dy;     // PNHWC output gradient (zero border), pitch dypitch
+  float* dw;           // fp32, dw[co*s_co + ci*s_ci + tap*s_tap] += ...
+  int xpitch, dypitch;
+  int Mtotal;          // rows of the padded linear space N*Hp*Wp
+  int Cout, Cin_real;  // bounds for the final scatter
+  int dy_c;            // channels physically present in dy (load bound)
+  int ntaps;
+  int tapoff[9];       // row offset of each tap (dr*Wp + ds)
+  int margin;          // max |tapoff|
+  long s_co, s_ci, s_tap;
+  int tiles_per_cta;   // pixel tiles per split
+  int n_tiles;         // total pixel tiles
+  int xrows, xpitch_b; // X window rows / chunk pitch in bytes
+  int precision;       // 3 or 1 (compile-time NPL mirrors this)
+};
+
+template <int PREC>
+__global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgradDev p) {
+  constexpr int NPL = (PREC == 3) ? 2 : 1;
+  constexpr int DY_CH = MCO / 8;                     // 16 chunks
+  constexpr int X_CH = NCI / 8;                      // 4 chunks
+  constexpr int DY_PITCH = (KT + 1) * 16;            // bytes per chunk (odd row count: conflict-free chunk-strided stores)
+  constexpr int DY_PLANE = DY_CH * DY_PITCH;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  const uint32_t bar_base = w_smem_u32(bars);
+  auto full = [&](int s) { return bar_base + 8u * s; };
+  auto empty = [&](int s) { return bar_base + 8u * (2 + s); };
+  const uint32_t accFull = bar_base + 8u * 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 48);
+  const int x_plane = X_CH * p.xpitch_b;
+  const int stage_bytes = NPL * (DY_PLANE + x_plane);
+  uint8_t* sbase = smem + 128;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co0 = blockIdx.x * MCO;
+  const int ci0 = blockIdx.y * NCI;
+  const int tile0 = blockIdx.z * p.tiles_per_cta;
+  const int tile1 = min(tile0 + p.tiles_per_cta, p.n_tiles);
+  const int my_tiles = tile1 - tile0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) { w_mbar_init(full(s), kWProdWarps * 32); w_mbar_init(empty(s), 1); }
+    w_mbar_init(accFull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kWProdWarps) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(w_smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kWProdWarps) {
+    // ============================ producers: fp32 rows -> bf16 hi/lo operand tiles ============================
+    const int tid = threadIdx.x;
+    constexpr int NPT = kWProdWarps * 32;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int st = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const int q0 = (tile0 + it) * KT;
+      w_mbar_wait(empty(st), ph ^ 1);
+      uint8_t* sdy = sbase + st * stage_bytes;
+      uint8_t* sx = sdy + NPL * DY_PLANE;
+      // dY tile: KT rows x 16 chunks
+      for (int item = tid; item < KT * DY_CH; item += NPT) {
+        const int c = item % DY_CH, e = item / DY_CH;
+        const int q = q0 + e;
+        float v[8];
+        if (q < p.Mtotal && co0 + c * 8 < p.dy_c) {
+          const float4* src = reinterpret_cast<const float4*>(p.dy + (size_t)q * p.dypitch + co0 + c * 8);
+          const float4 a = __ldg(src), b = __ldg(src + 1);
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        }
+        uint4 hi, lo;
+        split_bf16x2(v[0], v[1], hi.x, lo.x); split_bf16x2(v[2], v[3], hi.y, lo.y);
+        split_bf16x2(v[4], v[5], hi.z, lo.z); split_bf16x2(v[6], v[7], hi.w, lo.w);
+        *reinterpret_cast<uint4*>(sdy + c * DY_PITCH + e * 16) = hi;
+        if (NPL == 2) *reinterpret_cast<uint4*>(sdy + DY_PLANE + c * DY_PITCH + e * 16) = lo;
+      }
+      // X window: xrows rows x 4 chunks, rows q0 - margin ...
+      for (int item = tid; item < p.xrows * X_CH; item += NPT) {
+        const int c = item % X_CH, e = item / X_CH;
+        const int g = q0 - p.margin + e;
+        float v[8];
+        if (g >= 0 && g < p.Mtotal) {
+          const float4* src = reinterpret_cast<const float4*>(p.x + (size_t)g * p.xpitch + ci0 + c * 8);
+          const float4 a = __ldg(src), b = __ldg(src + 1);
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        }
+        uint4 hi, lo;
+        split_bf16x2(v[0], v[1], hi.x, lo.x); split_bf16x2(v[2], v[3], hi.y, lo.y);
+        split_bf16x2(v[4], v[5], hi.z, lo.z); split_bf16x2(v[6], v[7], hi.w, lo.w);
+        *reinterpret_cast<uint4*>(sx + c * p.xpitch_b + e * 16) = hi;
+        if (NPL == 2) *reinterpret_cast<uint4*>(sx + x_plane + c * p.xpitch_b + e * 16) = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      w_mbar_arrive(full(st));
+    }
+    // ============================ epilogue: TMEM -> dW (fp32 reductions) ============================
+    w_mbar_wait(accFull, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int quad = warp & 3, half = warp >> 2;
+    const int co = co0 + quad * 32 + lane;
+    for (int t = half; t < p.ntaps; t += 2) {
+      float v[32];
+      w_tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * NCI), v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (co < p.Cout && my_tiles > 0) {
+        float* dst = p.dw + (size_t)co * p.s_co + (size_t)t * p.s_tap;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int ci = ci0 + j;
+          if (ci < p.Cin_real) atomicAdd(dst + (size_t)ci * p.s_ci, v[j]);
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      // MN-major A and B (bits 15, 16), fp32 accumulate, bf16 inputs, N = 32, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NCI >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      for (int it = 0; it < my_tiles; ++it) {
+        const int st = it & 1;
+        w_mbar_wait(full(st), (it >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t dy_hi = w_smem_u32(sbase + st * stage_bytes);
+        const uint32_t dy_lo = dy_hi + DY_PLANE;
+        const uint32_t x_hi = dy_hi + NPL * DY_PLANE;
+        const uint32_t x_lo = x_hi + x_plane;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const uint32_t xoff = (uint32_t)(p.margin + p.tapoff[t]) * 16u;
+          const uint32_t d = tmem_base + (uint32_t)(t * NCI);
+#pragma unroll
+          for (int kk = 0; kk < KT / 16; ++kk) {
+            const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
+            // MN-major SWIZZLE_NONE: LBO = 128 B (next 8 K rows), SBO = chunk pitch (next 8 M/N channels)
+            const uint64_t ah = w_desc(dy_hi + kk * 256, 128u, DY_PITCH);
+            const uint64_t bh = w_desc(x_hi + xoff + kk * 256, 128u, (uint32_t)p.xpitch_b);
+            if (PREC == 3) {
+              const uint64_t al = w_desc(dy_lo + kk * 256, 128u, DY_PITCH);
+              const uint64_t bl = w_desc(x_lo + xoff + kk * 256, 128u, (uint32_t)p.xpitch_b);
+              w_umma(d, al, bh, idesc, acc);
+              w_umma(d, ah, bl, idesc, 1u);
+              w_umma(d, ah, bh, idesc, 1u);
+            } else {
+              w_umma(d, ah, bh, idesc, acc);
+            }
+          }
+        }
+        w_commit(empty(st));
+      }
+      w_commit(accFull);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == kWProdWarps) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+}  // namespace ddg
+
+using namespace ddg;
+
+extern "C" int ddg_conv2d_wgrad(const ddg_wgrad_desc* c, cudaStream_t stream) {
+  if (!c || !c->x || !c->dy || !c->dw || c->ntaps < 1 || c->ntaps > 9) { ddg_set_last_error("conv2d_wgrad: bad args"); return DDG_ERR_ARG; }
+  if (c->Cin_pad % NCI != 0 || c->xpitch % 4 != 0 || c->dypitch % 4 != 0 || c->dy_cpad % 8 != 0) {
+    ddg_set_last_error("conv2d_wgrad: channel counts must be padded (Cin to 32, pitches to 4)");
+    return DDG_ERR_ARG;
+  }
+  WgradDev d{};
+  d.x = c->x; d.dy = c->dy; d.dw = c->dw;
+  d.xpitch = c->xpitch; d.dypitch = c->dypitch;
+  d.Mtotal = c->N * c->Hp * c->Wp;
+  d.Cout = c->Cout;
+  d.dy_c = c->dy_cpad;
+  d.Cin_real = c->Cin_real;
+  d.ntaps = c->ntaps;
+  int margin = 0;
+  for (int t = 0; t < c->ntaps; ++t) {
+    d.tapoff[t] = c->tap_dr[t] * c->Wp + c->tap_ds[t];
+    const int a = d.tapoff[t] < 0 ? -d.tapoff[t] : d.tapoff[t];
+    if (a > margin) margin = a;
+  }
+  d.margin = margin;
+  d.s_co = c->s_co; d.s_ci = c->s_ci; d.s_tap = c->s_tap;
+  d.n_tiles = (d.Mtotal + KT - 1) / KT;
+  int rows = KT + 2 * margin;
+  d.xrows = rows;
+  if ((rows & 1) == 0) rows += 1;
+  d.xpitch_b = rows * 16;
+  const int prec = c->precision == 1 ? 1 : 3;
+  const int npl = prec == 3 ? 2 : 1;
+  const size_t stage = (size_t)npl * ((MCO / 8) * (KT + 1) * 16 + (NCI / 8) * d.xpitch_b);
+  const size_t smem = 128 + 2 * stage;
+  if (smem > 227 * 1024) { ddg_set_last_error("conv2d_wgrad: shared memory budget exceeded (image too wide)"); return DDG_ERR_UNSUPPORTED; }
+  const int gx = (c->Cout + MCO - 1) / MCO, gy = c->Cin_pad / NCI;
+  // split the pixel space so that the grid is ~2 waves of 148 SMs
+  int splits = (2 * 148 + gx * gy - 1) / (gx * gy);
+  if (splits > d.n_tiles) splits = d.n_tiles;
+  if (splits < 1) splits = 1;
+  d.tiles_per_cta = (d.n_tiles + splits - 1) / splits;
+  splits = (d.n_tiles + d.tiles_per_cta - 1) / d.tiles_per_cta;
+  dim3 grid(gx, gy, splits);
+  if (prec == 3) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+    wgrad_tc_kernel<3><<<grid, kWThreads, smem, stream>>>(d);
+  } else {
+    static bool attr1 = false;
+    if (!attr1) { cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr1 = true; }
+    wgrad_tc_kernel<1><<<grid, kWThreads, smem, stream>>>(d);
+  }
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}

@@ -30,6 +30,13 @@ class ConvDesc(C.Structure):
                 ('debug_prof', C.c_void_p), ('batch_rows', C.c_int)]
 
 
+class WgradDesc(C.Structure):
+    _fields_ = [('x', C.c_void_p), ('dy', C.c_void_p), ('dw', C.c_void_p), ('xpitch', C.c_int), ('dypitch', C.c_int),
+                ('N', C.c_int), ('Hp', C.c_int), ('Wp', C.c_int), ('Cout', C.c_int), ('dy_cpad', C.c_int),
+                ('Cin_real', C.c_int), ('Cin_pad', C.c_int), ('ntaps', C.c_int), ('tap_dr', C.c_int8 * 9),
+                ('tap_ds', C.c_int8 * 9), ('s_co', C.c_long), ('s_ci', C.c_long), ('s_tap', C.c_long), ('precision', C.c_int)]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_long, C.c_float
 
 _SIGNATURES = {
@@ -47,7 +54,7 @@ _SIGNATURES = {
     'ddg_nchw_to_pnhwc': ([_P, _I, _P, _I, _P, _I, _I, _I, _I, _F, _F, _P], _I),
     'ddg_pnhwc_to_nchw': ([_P, _P] + [_I] * 6 + [_P], _I),
     'ddg_gn_prepare': ([_P, _I, _P, _I, _P, _P, _I, _I, _P, _P, _I, _I, _I, _F, _P], _I),
-    'ddg_fir_pnhwc': ([_P, _P, _P, _I, _P] + [_I] * 6 + [_P, _P], _I),
+    'ddg_fir_pnhwc': ([_P, _P, _P, _I, _P] + [_I] * 6 + [_F, _P], _I),
     'ddg_minibatch_stddev': ([_P, _P] + [_I] * 6 + [_P], _I),
     'ddg_spatial_sum': ([_P, _P] + [_I] * 5 + [_P], _I),
     'ddg_softmax_rows': ([_P, _P, _L, _I, _I, _I, _P], _I),
@@ -55,6 +62,11 @@ _SIGNATURES = {
     'ddg_conv_packed_bytes': ([_I, _I, _I, _I], _L),
     'ddg_conv_pack_weights': ([_P, _P, _I, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _I, _I, _L, _P], _I),
     'ddg_conv2d_fwd': ([C.POINTER(ConvDesc), _P], _I),
+    'ddg_conv2d_wgrad': ([C.POINTER(WgradDesc), _P], _I),
+    'ddg_affine_act_fwd': ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
+    'ddg_affine_act_bwd': ([_P] * 6 + [_I] * 5 + [_P], _I),
+    'ddg_stats_fwd': ([_P, _P, _I, _I, _I, _I, _P], _I),
+    'ddg_stats_bwd': ([_P, _P, _P, _I, _I, _I, _I, _P], _I),
 }
 
 _lib = None

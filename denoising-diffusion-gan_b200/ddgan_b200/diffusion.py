@@ -78,9 +78,15 @@ def q_sample_pairs(coeff, x_start, t, noise_xt=None, noise_xtp1=None):
 
 
 def sample_posterior(coefficients, x_0, x_t, t, noise=None, out=None):
-    """ddgan.py:152-169."""
+    """ddgan.py:152-169.  Under autograd (training: x_0 = G(...) carries a graph) the three-term update is expressed with
+    differentiable elementwise ops; otherwise it is the single fused kernel."""
     if noise is None:
         noise = torch.randn_like(x_t)
+    if torch.is_grad_enabled() and (x_0.requires_grad or x_t.requires_grad):
+        shp = (-1,) + (1,) * (x_t.dim() - 1)
+        mean = coefficients.posterior_mean_coef1[t].view(shp) * x_0 + coefficients.posterior_mean_coef2[t].view(shp) * x_t
+        sd = (t != 0).float().view(shp) * torch.exp(0.5 * coefficients.posterior_log_variance_clipped[t].view(shp))
+        return mean + sd * noise
     return ops.sample_posterior(x_0, x_t, noise, t, coefficients.posterior_mean_coef1, coefficients.posterior_mean_coef2,
                                 coefficients.posterior_log_variance_clipped, out=out)
 

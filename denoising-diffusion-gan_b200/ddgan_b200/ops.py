@@ -189,12 +189,65 @@ def gn_prepare(stats_a, ca, stats_b, cb, gamma, beta, gb_stride, per_sample, n, 
                                ptr(scale), ptr(shift), n, hw, groups, eps, stream()), 'gn_prepare')
 
 
-def fir_pnhwc(x, mode, out, scale=None, shift=None, act=ACT_NONE):
-    """mode 1 up2, 2 down2, 3 pad(2,2)+space-to-depth.  x [N,H+2,W+2,C]."""
+def fir_pnhwc(x, mode, out, scale=None, shift=None, act=ACT_NONE, gain=1.0):
+    """mode 1 up2, 2 down2, 3 pad(2,2)+space-to-depth, 4 adjoint of 3 (x is the s2d tensor, out the image)."""
+    if mode == 4:
+        n, hp, wp, c = out.shape
+        check(lib().ddg_fir_pnhwc(ptr(x), None, None, ACT_NONE, ptr(out), n, hp - 2, wp - 2, c, 4, x.shape[-1], gain, stream()),
+              'fir_pnhwc')
+        return out
     n, hp, wp, c = x.shape
-    check(lib().ddg_fir_pnhwc(ptr(x), ptr(scale), ptr(shift), act, ptr(out), n, hp - 2, wp - 2, c, mode, out.shape[-1], None,
+    check(lib().ddg_fir_pnhwc(ptr(x), ptr(scale), ptr(shift), act, ptr(out), n, hp - 2, wp - 2, c, mode, out.shape[-1], gain,
                               stream()), 'fir_pnhwc')
     return out
+
+
+def affine_act_fwd(x, scale, shift, act, out=None):
+    n, hp, wp, c = x.shape
+    if out is None:
+        out = torch.zeros_like(x)
+    check(lib().ddg_affine_act_fwd(ptr(x), ptr(scale), ptr(shift), ptr(out), n, hp - 2, wp - 2, c, act, stream()), 'affine_act_fwd')
+    return out
+
+
+def affine_act_bwd(x, dy, scale, shift, act, need_sums=True):
+    n, hp, wp, c = x.shape
+    dx = torch.zeros_like(x)
+    sums = torch.zeros(n, c, 2, dtype=torch.float64, device=x.device) if need_sums else None
+    check(lib().ddg_affine_act_bwd(ptr(x), ptr(dy), ptr(scale), ptr(shift), ptr(dx), ptr(sums), n, hp - 2, wp - 2, c, act, stream()),
+          'affine_act_bwd')
+    return dx, sums
+
+
+def stats_fwd(x):
+    n, hp, wp, c = x.shape
+    st = torch.zeros(n, c, 2, dtype=torch.float64, device=x.device)
+    check(lib().ddg_stats_fwd(ptr(x), ptr(st), n, hp - 2, wp - 2, c, stream()), 'stats_fwd')
+    return st
+
+
+def stats_bwd(x, g):
+    n, hp, wp, c = x.shape
+    dx = torch.zeros_like(x)
+    check(lib().ddg_stats_bwd(ptr(x), ptr(g), ptr(dx), n, hp - 2, wp - 2, c, stream()), 'stats_bwd')
+    return dx
+
+
+def conv_wgrad(x, dy, dw, n, hp, wp, cout, cin_real, cin_pad, taps, s_co, s_ci, s_tap, precision=3, xpitch=None, dypitch=None,
+               dy_cpad=None, x_elem_offset=0):
+    """dw[co*s_co + ci*s_ci + t*s_tap] += sum_q dy[q][co] * x[q + tap_t][ci]  (dw zero-initialised by the caller)."""
+    d = _lib.WgradDesc()
+    d.x = x.data_ptr() + 4 * x_elem_offset; d.dy = ptr(dy); d.dw = ptr(dw)
+    d.xpitch = xpitch or x.shape[-1]; d.dypitch = dypitch or dy.shape[-1]
+    d.N, d.Hp, d.Wp = n, hp, wp
+    d.Cout = cout; d.dy_cpad = dy_cpad or dy.shape[-1]; d.Cin_real = cin_real; d.Cin_pad = cin_pad
+    d.ntaps = len(taps)
+    for t, (dr, ds) in enumerate(taps):
+        d.tap_dr[t] = dr; d.tap_ds[t] = ds
+    d.s_co, d.s_ci, d.s_tap = s_co, s_ci, s_tap
+    d.precision = precision
+    check(lib().ddg_conv2d_wgrad(C.byref(d), stream()), 'conv2d_wgrad')
+    return dw
 
 
 def minibatch_stddev(x, out, group):

@@ -1,0 +1,497 @@
+"""Differentiable (training) forwards of NCSNpp / Discriminator_* built from autograd Functions over the sm_100a kernels.
+
+The adversarial step (ddgan.py:443-518) needs first-order gradients of G and D and, every `lazy_reg` steps, the
+double-backward of D for the R1 penalty (ddgan.py:462-467).  The heavy operators are closed under differentiation:
+
+    ConvFn   (implicit-GEMM forward)      backward -> DgradFn (w.r.t. x), WgradFn (w.r.t. w)
+    DgradFn  (conv with adjoint taps)     backward -> ConvFn  (w.r.t. dy), WgradFn (w.r.t. w)
+    WgradFn  (tcgen05 weight gradient)    backward -> DgradFn (w.r.t. x),  ConvFn  (w.r.t. dy)
+    FirFn    (up / down / pad FIR)        backward -> FirFn with the adjoint mode and gain (upfirdn2d.py:119-122 analogue)
+    ToPnhwcFn <-> FromPnhwcFn             layout changes at the model boundary
+
+so `torch.autograd.grad(..., create_graph=True)` through D just records more of the same kernels.  GroupNorm / AdaGN is
+decomposed as  StatsFn (per-(n,c) sums)  ->  tiny [N,C] algebra in torch (float64)  ->  AffineActFn (scale/shift + SiLU),
+which makes autograd assemble the exact GroupNorm gradient.  Elementwise glue on activations (residual add, 1/sqrt2, cat,
+LeakyReLU, tanh) and the attention core stay torch ops in this first training path; inference uses the fully fused plan in
+engine.py instead.  Activations are PNHWC ([N,H+2,W+2,C], zero border); every op here preserves the zero border.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import torch
+import torch.nn.functional as F
+from torch.autograd import Function
+
+from . import arch, ops
+
+RSQRT2 = 1.0 / math.sqrt(2.0)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# layout boundary
+# ------------------------------------------------------------------------------------------------------------------
+class ToPnhwcFn(Function):
+    @staticmethod
+    def forward(ctx, x, cpad):
+        ctx.c = x.shape[1]
+        return ops.to_pnhwc(x.contiguous(), cpad=cpad)
+
+    @staticmethod
+    def backward(ctx, g):
+        return FromPnhwcFn.apply(g, ctx.c), None
+
+
+class FromPnhwcFn(Function):
+    @staticmethod
+    def forward(ctx, x, c):
+        ctx.cpad = x.shape[-1]
+        return ops.from_pnhwc(x.contiguous(), c)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ToPnhwcFn.apply(g, ctx.cpad), None
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# convolution family
+# ------------------------------------------------------------------------------------------------------------------
+def conv_spec(w_shape, taps, n, hout, wout, cpad_in, s_co, s_ci, s_tap, cout, cin, hp=None, wp=None, out_nchw=False, prec=3):
+    return SimpleNamespace(w_shape=tuple(w_shape), taps=list(taps), n=n, hout=hout, wout=wout, hp=hp or hout + 2,
+                           wp=wp or wout + 2, cpad_in=cpad_in, s_co=s_co, s_ci=s_ci, s_tap=s_tap, cout=cout, cin=cin,
+                           out_nchw=out_nchw, prec=prec, cpad_out=ops.pad_c(cout))
+
+
+def _conv_forward(x, w, bias, addvec, sp):
+    cw = ops.ConvWeights(sp.cout, [(sp.cpad_in, len(sp.taps))], x.device, precision=sp.prec)
+    cw.pack_segment(0, w, sp.cin, sp.s_co, sp.s_ci, sp.s_tap)
+    if sp.out_nchw:
+        out = torch.zeros(sp.n, sp.cout, sp.hout, sp.wout, device=x.device)
+        mode, out_c = ops.OUT_NCHW, 0
+    else:
+        out = ops.alloc_pnhwc(sp.n, sp.hout, sp.wout, sp.cpad_out, x.device)
+        mode, out_c = ops.OUT_PNHWC, sp.cpad_out
+    ops.conv2d_fused(cw, [ops.conv_src(x, sp.cpad_in, sp.taps)], sp.n, sp.hout, sp.wout, out, out_mode=mode, out_c=out_c,
+                     hp=sp.hp, wp=sp.wp, bias=bias, addvec=addvec, addvec_stride=(addvec.shape[1] if addvec is not None else 0))
+    return out
+
+
+def _embed(t, hp, wp):
+    """Place a PNHWC tensor into a (possibly larger) zero padded space [N,hp,wp,C] (top-left aligned)."""
+    if t.shape[1] == hp and t.shape[2] == wp:
+        return t
+    return F.pad(t, (0, 0, 0, wp - t.shape[2], 0, hp - t.shape[1]))
+
+
+def _crop(t, hp, wp):
+    return t if (t.shape[1] == hp and t.shape[2] == wp) else t[:, :hp, :wp, :].contiguous()
+
+
+class ConvFn(Function):
+    """y = conv(x; w) + bias + addvec[n, c]   (x, y PNHWC; y NCHW when sp.out_nchw)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, addvec, sp):
+        x = x.contiguous()
+        w = w.contiguous()
+        ctx.sp = sp
+        ctx.has_bias, ctx.has_addvec = bias is not None, addvec is not None
+        ctx.save_for_backward(x, w)
+        return _conv_forward(x, w, bias, addvec.contiguous() if addvec is not None else None, sp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        sp = ctx.sp
+        if sp.out_nchw:
+            dy = ToPnhwcFn.apply(dy, sp.cpad_out)
+        dyc = dy.contiguous()
+        dx = DgradFn.apply(dyc, w, sp) if ctx.needs_input_grad[0] else None
+        dw = WgradFn.apply(x, dyc, sp) if ctx.needs_input_grad[1] else None
+        db = dyc.sum(dim=(0, 1, 2))[:sp.cout] if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        dav = dyc.sum(dim=(1, 2))[:, :sp.cout] if (ctx.has_addvec and ctx.needs_input_grad[3]) else None
+        return dx, dw, db, dav, None
+
+
+class DgradFn(Function):
+    """dx[q] = sum_t W_t^T dy[q - off_t]: the same implicit-GEMM kernel with adjoint taps and the transposed operand."""
+
+    @staticmethod
+    def forward(ctx, dy, w, sp):
+        ctx.sp = sp
+        dy = dy.contiguous()
+        w = w.contiguous()
+        ctx.save_for_backward(dy, w)
+        # output space = the conv's input space (hp x wp padded); dy is embedded into it when the spaces differ (2x2-tap conv)
+        dye = _embed(dy, sp.hp, sp.wp).contiguous()
+        cy = dye.shape[-1]
+        cw = ops.ConvWeights(sp.cpad_in, [(cy, len(sp.taps))], dy.device, precision=sp.prec)
+        cw.pack_segment(0, w, sp.cout, sp.s_ci, sp.s_co, sp.s_tap)   # roles of co / ci swapped
+        dx = ops.alloc_pnhwc(sp.n, sp.hp - 2, sp.wp - 2, sp.cpad_in, dy.device)
+        taps = [(-dr, -ds) for dr, ds in sp.taps]
+        ops.conv2d_fused(cw, [ops.conv_src(dye, cy, taps)], sp.n, sp.hp - 2, sp.wp - 2, dx)
+        if sp.cin < sp.cpad_in:
+            dx[..., sp.cin:] = 0
+        return dx
+
+    @staticmethod
+    def backward(ctx, ggx):
+        dy, w = ctx.saved_tensors
+        sp = ctx.sp
+        ggx = ggx.contiguous()
+        g_dy = g_w = None
+        if ctx.needs_input_grad[0]:
+            spf = SimpleNamespace(**{**vars(sp), 'out_nchw': False})
+            g_dy = ConvFn.apply(ggx, w, None, None, spf)
+        if ctx.needs_input_grad[1]:
+            g_w = WgradFn.apply(ggx, dy, sp)
+        return g_dy, g_w, None
+
+
+class WgradFn(Function):
+    """dw[co][ci][t] = sum_q dy[q][co] x[q + off_t][ci]  (tcgen05 wgrad kernel, split-K with fp32 reductions)."""
+
+    @staticmethod
+    def forward(ctx, x, dy, sp):
+        ctx.sp = sp
+        x = x.contiguous()
+        dy = dy.contiguous()
+        ctx.save_for_backward(x, dy)
+        dye = _embed(dy, sp.hp, sp.wp).contiguous()
+        dw = torch.zeros(sp.w_shape, device=x.device)
+        ops.conv_wgrad(x, dye, dw, sp.n, sp.hp, sp.wp, sp.cout, sp.cin, sp.cpad_in, sp.taps, sp.s_co, sp.s_ci, sp.s_tap,
+                       precision=sp.prec)
+        return dw
+
+    @staticmethod
+    def backward(ctx, gdw):
+        x, dy = ctx.saved_tensors
+        sp = ctx.sp
+        gdw = gdw.contiguous()
+        g_x = g_dy = None
+        if ctx.needs_input_grad[0]:
+            g_x = DgradFn.apply(dy, gdw, sp)
+        if ctx.needs_input_grad[1]:
+            spf = SimpleNamespace(**{**vars(sp), 'out_nchw': False})
+            g_dy = _crop(ConvFn.apply(x, gdw, None, None, spf), dy.shape[1], dy.shape[2])
+        return g_x, g_dy, None
+
+
+def conv3x3(x, w, b, n, h, wd, addvec=None, out_nchw=False, prec=3):
+    """nn.Conv2d(k=3, s=1, p=1) on PNHWC; w [Cout, Cin, 3, 3] (zero-padded along Cin to x's channel count if needed)."""
+    cout, cin = w.shape[0], w.shape[1]
+    cp = x.shape[-1]
+    if cin < cp:
+        w = F.pad(w, (0, 0, 0, 0, 0, cp - cin))
+    sp = conv_spec(w.shape, ops.TAPS_3X3, n, h, wd, cp, cp * 9, 9, 1, cout, cp, out_nchw=out_nchw, prec=prec)
+    return ConvFn.apply(x, w, b, addvec, sp)
+
+
+def conv1x1(x, w, b, n, h, wd, prec=3):
+    """1x1 conv; w [Cout, Cin, 1, 1] or [Cout, Cin]."""
+    cout, cin = w.shape[0], w.shape[1]
+    cp = x.shape[-1]
+    w2 = w.reshape(cout, cin)
+    if cin < cp:
+        w2 = F.pad(w2, (0, cp - cin))
+    sp = conv_spec(w2.shape, ops.TAPS_1X1, n, h, wd, cp, cp, 1, 0, cout, cp, prec=prec)
+    return ConvFn.apply(x, w2, b, None, sp)
+
+
+def nin(x, W, b, n, h, wd, prec=3):
+    """layers.py:489-512: weight stored [in, out]."""
+    cin, cout = W.shape
+    sp = conv_spec(W.shape, ops.TAPS_1X1, n, h, wd, x.shape[-1], 1, cout, 0, cout, cin, prec=prec)
+    return ConvFn.apply(x, W, b, None, sp)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# FIR resampling
+# ------------------------------------------------------------------------------------------------------------------
+class FirFn(Function):
+    """mode 1: up x2 (gain 4 built in), 2: down x2, 3: pad(2,2) + space-to-depth, 4: adjoint of 3; `gain` scales the taps."""
+
+    @staticmethod
+    def forward(ctx, x, mode, gain, c_img):
+        ctx.mode, ctx.gain, ctx.c_img = mode, gain, c_img
+        x = x.contiguous()
+        n, hp, wp, c = x.shape
+        if mode == 1:
+            out = ops.alloc_pnhwc(n, 2 * (hp - 2), 2 * (wp - 2), c, x.device)
+        elif mode == 2:
+            out = ops.alloc_pnhwc(n, (hp - 2) // 2, (wp - 2) // 2, c, x.device)
+        elif mode == 3:
+            out = torch.zeros(n, (hp - 2) // 2 + 3, (wp - 2) // 2 + 3, 4 * c, device=x.device)
+        else:
+            out = ops.alloc_pnhwc(n, 2 * (hp - 3), 2 * (wp - 3), c_img, x.device)
+        ctx.in_c = c
+        ops.fir_pnhwc(x, mode, out, gain=gain)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        adj = {1: (2, 4.0 * ctx.gain), 2: (1, 0.25 * ctx.gain), 3: (4, ctx.gain), 4: (3, ctx.gain)}[ctx.mode]
+        return FirFn.apply(g, adj[0], adj[1], ctx.in_c), None, None, None
+
+
+def fir_up(x):
+    return FirFn.apply(x, 1, 1.0, 0)
+
+
+def fir_down(x):
+    return FirFn.apply(x, 2, 1.0, 0)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GroupNorm = stats + [N,C] algebra + affine/activation
+# ------------------------------------------------------------------------------------------------------------------
+class StatsFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        ctx.save_for_backward(x)
+        return ops.stats_fwd(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, = ctx.saved_tensors
+        return ops.stats_bwd(x, g.to(torch.float32).contiguous())
+
+
+class AffineActFn(Function):
+    @staticmethod
+    def forward(ctx, x, scale, shift, act):
+        x, scale, shift = x.contiguous(), scale.contiguous(), shift.contiguous()
+        ctx.act = act
+        ctx.save_for_backward(x, scale, shift)
+        return ops.affine_act_fwd(x, scale, shift, act)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, scale, shift = ctx.saved_tensors
+        dx, sums = ops.affine_act_bwd(x, dy.contiguous(), scale, shift, ctx.act)
+        return dx, sums[..., 0].to(torch.float32), sums[..., 1].to(torch.float32), None
+
+
+def group_norm_act(x, h, w, groups, gamma, beta, act, eps=1e-6):
+    """gamma / beta: [N, C] (AdaGN) or [C] (affine GroupNorm).  Statistics in float64 as in the fused plan."""
+    n, c = x.shape[0], x.shape[-1]
+    cpg = c // groups
+    st = StatsFn.apply(x).view(n, groups, cpg, 2).sum(2)
+    cnt = float(cpg * h * w)
+    mean = st[..., 0] / cnt
+    var = (st[..., 1] / cnt - mean * mean).clamp_min(0.0)
+    rstd = torch.rsqrt(var + eps)
+    mean_c = mean.repeat_interleave(cpg, dim=1)
+    rstd_c = rstd.repeat_interleave(cpg, dim=1)
+    g64 = gamma.double() if gamma.dim() == 2 else gamma.double().unsqueeze(0)
+    b64 = beta.double() if beta.dim() == 2 else beta.double().unsqueeze(0)
+    scale = (g64 * rstd_c).to(torch.float32)
+    shift = (b64 - mean_c * g64 * rstd_c).to(torch.float32)
+    if scale.shape[0] != n:
+        scale, shift = scale.expand(n, c), shift.expand(n, c)
+    return AffineActFn.apply(x, scale, shift, act)
+
+
+class LinearFn(Function):
+    """y = x W^T + b on [N, K] rows through ddg_linear (forward and both gradient GEMMs)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        x, W = x.contiguous(), W.contiguous()
+        ctx.save_for_backward(x, W)
+        ctx.has_b = b is not None
+        return ops.linear(x, W, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = ops.linear(dy, W.t().contiguous()) if ctx.needs_input_grad[0] else None
+        dW = ops.linear(dy.t().contiguous(), x.t().contiguous()) if ctx.needs_input_grad[1] else None
+        db = dy.sum(0) if (ctx.has_b and ctx.needs_input_grad[2]) else None
+        return dx, dW, db
+
+
+def _groups(c):
+    return min(c // 4, 32)
+
+
+def _interior(x):
+    return x[:, 1:-1, 1:-1, :]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# generator
+# ------------------------------------------------------------------------------------------------------------------
+def generator_forward(mod, x, time_cond, z):
+    """NCSNpp.forward (ncsnpp_generator_adagn.py:280-431), training path.  `mod` is ddgan_b200.modules.NCSNpp."""
+    cfg = mod.cfg
+    if not (cfg.resblock_type == 'biggan' and cfg.embedding_type == 'positional' and cfg.progressive == 'none'
+            and cfg.progressive_input in ('residual', 'none') and cfg.fir and cfg.conditional):
+        raise NotImplementedError('training path covers the biggan / positional / fir configuration family')
+    P = dict(mod.named_parameters())
+    prec = mod.precision
+    N, S = x.shape[0], cfg.image_size
+    nf = cfg.num_channels_dae
+    drop = float(cfg.dropout) if mod.training else 0.0
+
+    # z mapping and time embedding
+    zn = z / torch.sqrt(torch.mean(z ** 2, dim=1, keepdim=True) + 1e-8)
+    zemb = F.silu(LinearFn.apply(zn, P['z_transform.1.weight'], P['z_transform.1.bias']))
+    for i in range(cfg.n_mlp):
+        zemb = F.silu(LinearFn.apply(zemb, P[f'z_transform.{3 + 2 * i}.weight'], P[f'z_transform.{3 + 2 * i}.bias']))
+    temb = ops.timestep_embedding(time_cond, nf)
+    temb = LinearFn.apply(temb, P['all_modules.0.weight'], P['all_modules.0.bias'])
+    temb = LinearFn.apply(F.silu(temb), P['all_modules.1.weight'], P['all_modules.1.bias'])
+    temb_act = F.silu(temb)
+
+    def adagn(t, h, w, prefix, act=ops.ACT_SILU):
+        c = t.shape[-1]
+        style = LinearFn.apply(zemb, P[prefix + '.style.weight'], P[prefix + '.style.bias'])
+        return group_norm_act(t, h, w, _groups(c), style[:, :c], style[:, c:], act)
+
+    def resblock(m, t, h, w):
+        pn = f"all_modules.{m['idx']}."
+        cin, cout = m['i'], m['o']
+        hh = adagn(t, h, w, pn + 'GroupNorm_0')
+        xs = t
+        if m['up']:
+            hh, xs, h, w = fir_up(hh), fir_up(xs), 2 * h, 2 * w
+        elif m['down']:
+            hh, xs, h, w = fir_down(hh), fir_down(xs), h // 2, w // 2
+        dense = LinearFn.apply(temb_act, P[pn + 'Dense_0.weight'], P[pn + 'Dense_0.bias'])
+        hh = conv3x3(hh, P[pn + 'Conv_0.weight'], P[pn + 'Conv_0.bias'], N, h, w, addvec=dense, prec=prec)
+        hh = adagn(hh, h, w, pn + 'GroupNorm_1')
+        if drop > 0:
+            hh = F.dropout(hh, drop, True)
+        hh = conv3x3(hh, P[pn + 'Conv_1.weight'], P[pn + 'Conv_1.bias'], N, h, w, prec=prec)
+        if cin != cout or m['up'] or m['down']:
+            xs = conv1x1(xs, P[pn + 'Conv_2.weight'], P[pn + 'Conv_2.bias'], N, h, w, prec=prec)
+        out = xs + hh
+        return (out * RSQRT2 if cfg.skip_rescale else out), h, w
+
+    def attn(m, t, h, w):
+        pn = f"all_modules.{m['idx']}."
+        c = t.shape[-1]
+        g = group_norm_act(t, h, w, _groups(c), P[pn + 'GroupNorm_0.weight'], P[pn + 'GroupNorm_0.bias'], ops.ACT_NONE)
+        q = _interior(nin(g, P[pn + 'NIN_0.W'], P[pn + 'NIN_0.b'], N, h, w, prec)).reshape(N, h * w, c)
+        k = _interior(nin(g, P[pn + 'NIN_1.W'], P[pn + 'NIN_1.b'], N, h, w, prec)).reshape(N, h * w, c)
+        v = _interior(nin(g, P[pn + 'NIN_2.W'], P[pn + 'NIN_2.b'], N, h, w, prec)).reshape(N, h * w, c)
+        a = torch.softmax(torch.bmm(q, k.transpose(1, 2)) * (int(c) ** (-0.5)), dim=-1)
+        o = torch.bmm(a, v).reshape(N, h, w, c)
+        o = F.pad(o, (0, 0, 1, 1, 1, 1))
+        o = nin(o, P[pn + 'NIN_3.W'], P[pn + 'NIN_3.b'], N, h, w, prec)
+        out = t + o
+        return out * RSQRT2 if cfg.skip_rescale else out
+
+    def pyramid_down(m, pyr, hcur, h, w):
+        """conv_downsample_2d + bias, then (pyramid + h)/sqrt2 (ncsnpp...:343-350); h, w = input size of pyr."""
+        pn = f"all_modules.{m['idx']}.Conv2d_0"
+        cp = pyr.shape[-1]
+        ho, wo = h // 2, w // 2
+        s2d = FirFn.apply(pyr, 3, 1.0, 0)                       # [N, ho+3, wo+3, 4*cp]
+        wt = P[pn + '.weight']
+        cout, cin = wt.shape[0], wt.shape[1]
+        w2 = wt.new_zeros(cout, 2, 2, cp, 2, 2)
+        for dy in range(2):
+            for dx in range(2):
+                for py in range(2):
+                    for px in range(2):
+                        r, s_ = 2 * dy + py, 2 * dx + px
+                        if r < 3 and s_ < 3:
+                            w2[:, py, px, :cin, dy, dx] = wt[:, :, r, s_]
+        w2 = w2.reshape(cout, 4 * cp, 4)
+        sp = conv_spec(w2.shape, ops.TAPS_2X2, N, ho, wo, 4 * cp, 4 * cp * 4, 4, 1, cout, 4 * cp, hp=ho + 3, wp=wo + 3, prec=prec)
+        y = ConvFn.apply(s2d, w2, P[pn + '.bias'], None, sp)
+        out = y + hcur
+        return out * RSQRT2 if cfg.skip_rescale else out
+
+    mods = arch.ncsnpp_modules(cfg)
+    xin = x if cfg.centered else 2 * x - 1.0
+    xp = ToPnhwcFn.apply(xin, ops.pad_c(cfg.num_channels))
+    m0 = mods[2]
+    h = conv3x3(xp, P[f"all_modules.{m0['idx']}.weight"], P[f"all_modules.{m0['idx']}.bias"], N, S, S, prec=prec)
+    hs = [(h, S)]
+    pyramid, pyr_size = xp, S
+    rest = mods[3:]
+    i = 0
+    nres = len(cfg.ch_mult)
+    cur = S
+    for lvl in range(nres):
+        for _ in range(cfg.num_res_blocks):
+            m = rest[i]; i += 1
+            h, _, _ = resblock(m, hs[-1][0], cur, cur)
+            if cur in cfg.attn_resolutions:
+                h = attn(rest[i], h, cur, cur); i += 1
+            hs.append((h, cur))
+        if lvl != nres - 1:
+            m = rest[i]; i += 1
+            h, nh, _ = resblock(m, hs[-1][0], cur, cur)
+            if cfg.progressive_input == 'residual':
+                m = rest[i]; i += 1
+                h = pyramid_down(m, pyramid, h, pyr_size, pyr_size)
+                pyramid, pyr_size = h, nh
+            cur = nh
+            hs.append((h, cur))
+    h = hs[-1][0]
+    h, _, _ = resblock(rest[i], h, cur, cur); i += 1
+    h = attn(rest[i], h, cur, cur); i += 1
+    h, _, _ = resblock(rest[i], h, cur, cur); i += 1
+    for lvl in reversed(range(nres)):
+        for _ in range(cfg.num_res_blocks + 1):
+            skip, _ = hs.pop()
+            h, _, _ = resblock(rest[i], torch.cat([h, skip], dim=-1), cur, cur); i += 1
+        if cur in cfg.attn_resolutions:
+            h = attn(rest[i], h, cur, cur); i += 1
+        if lvl != 0:
+            h, cur, _ = resblock(rest[i], h, cur, cur); i += 1
+    assert not hs
+    g, c = rest[i], rest[i + 1]
+    h = group_norm_act(h, cur, cur, _groups(h.shape[-1]), P[f"all_modules.{g['idx']}.weight"], P[f"all_modules.{g['idx']}.bias"],
+                       ops.ACT_SILU)
+    y = conv3x3(h, P[f"all_modules.{c['idx']}.weight"], P[f"all_modules.{c['idx']}.bias"], N, cur, cur, out_nchw=True, prec=prec)
+    return y if cfg.not_use_tanh else torch.tanh(y)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# discriminators
+# ------------------------------------------------------------------------------------------------------------------
+def discriminator_forward(mod, x, t, x_t):
+    """Discriminator_small/large.forward (discriminator.py:134-167 / :205-238), training path (double-differentiable)."""
+    P = dict(mod.named_parameters())
+    prec = mod.precision
+    N, S = x.shape[0], x.shape[-1]
+    te = ops.timestep_embedding(t, mod.t_emb_dim)
+    te = F.linear(te, P['t_embed.main.0.weight'], P['t_embed.main.0.bias'])
+    te = F.linear(F.leaky_relu(te, 0.2), P['t_embed.main.2.weight'], P['t_embed.main.2.bias'])
+    te = F.leaky_relu(te, 0.2)
+    xin = ToPnhwcFn.apply(torch.cat((x, x_t), dim=1), ops.pad_c(mod.nc))
+    h = conv1x1(xin, P['start_conv.weight'], P['start_conv.bias'], N, S, S, prec=prec)
+    cur = S
+    for i, (a, b, ds) in enumerate(arch.discriminator_blocks(mod.ngf, mod.large)):
+        pn = f'conv{i + 1}.'
+        dense = F.linear(te, P[pn + 'dense_t1.weight'], P[pn + 'dense_t1.bias'])
+        o = conv3x3(F.leaky_relu(h, 0.2), P[pn + 'conv1.0.weight'], P[pn + 'conv1.0.bias'], N, cur, cur, addvec=dense, prec=prec)
+        o = F.leaky_relu(o, 0.2)
+        xs = h
+        if ds:
+            o, xs, cur = fir_down(o), fir_down(xs), cur // 2
+        o = conv3x3(o, P[pn + 'conv2.0.weight'], P[pn + 'conv2.0.bias'], N, cur, cur, prec=prec)
+        sk = conv1x1(xs, P[pn + 'skip.0.weight'], None, N, cur, cur, prec=prec)
+        h = (o + sk) * RSQRT2
+    # minibatch stddev (discriminator.py:150-158) on the interior, appended as one extra (32-padded) channel group
+    c = h.shape[-1]
+    group = min(N, mod.stddev_group)
+    inner = _interior(h)                                            # [N, H, W, C]
+    sd = inner.reshape(group, -1, cur, cur, c)
+    sd = torch.sqrt(sd.var(0, unbiased=False) + 1e-8).mean(dim=(1, 2, 3))   # [N/group]
+    sd = sd.repeat(group)                                           # sample i -> stat-set i % (N/group)
+    extra = h.new_zeros(N, cur, cur, 32)
+    extra = torch.cat([sd.view(N, 1, 1, 1).expand(N, cur, cur, 1), extra[..., 1:]], dim=-1)
+    extra = F.pad(extra, (0, 0, 1, 1, 1, 1))
+    hcat = torch.cat([h, extra], dim=-1)
+    f = conv3x3(hcat, P['final_conv.weight'], P['final_conv.bias'], N, cur, cur, prec=prec)
+    f = F.leaky_relu(_interior(f), 0.2).sum(dim=(1, 2))            # [N, C]
+    return F.linear(f, P['end_linear.weight'], P['end_linear.bias'])

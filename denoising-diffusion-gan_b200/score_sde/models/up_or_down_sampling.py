@@ -1,0 +1,51 @@
+"""FIR resampling layers on the public NCHW surface (reference: score_sde/models/up_or_down_sampling.py:149-262).
+Inside the fused engines these are folded into PNHWC kernels; the functions here serve external callers and tests."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from score_sde.op import upfirdn2d
+
+
+def _setup_kernel(k):
+    k = np.asarray(k, dtype=np.float32)
+    if k.ndim == 1:
+        k = np.outer(k, k)
+    k /= np.sum(k)
+    assert k.ndim == 2 and k.shape[0] == k.shape[1]
+    return k
+
+
+def upsample_2d(x, k=None, factor=2, gain=1):
+    assert isinstance(factor, int) and factor >= 1
+    k = _setup_kernel([1] * factor if k is None else k) * (gain * (factor ** 2))
+    p = k.shape[0] - factor
+    return upfirdn2d(x, torch.tensor(k, device=x.device), up=factor, pad=((p + 1) // 2 + factor - 1, p // 2))
+
+
+def downsample_2d(x, k=None, factor=2, gain=1):
+    assert isinstance(factor, int) and factor >= 1
+    k = _setup_kernel([1] * factor if k is None else k) * gain
+    p = k.shape[0] - factor
+    return upfirdn2d(x, torch.tensor(k, device=x.device), down=factor, pad=((p + 1) // 2, p // 2))
+
+
+def conv_downsample_2d(x, w, k=None, factor=2, gain=1):
+    assert isinstance(factor, int) and factor >= 1
+    _outC, _inC, convH, convW = w.shape
+    assert convW == convH
+    k = _setup_kernel([1] * factor if k is None else k) * gain
+    p = (k.shape[0] - factor) + (convW - 1)
+    x = upfirdn2d(x, torch.tensor(k, device=x.device), pad=((p + 1) // 2, p // 2))
+    return F.conv2d(x, w, stride=factor, padding=0)
+
+
+def naive_upsample_2d(x, factor=2):
+    _N, C, H, W = x.shape
+    x = torch.reshape(x, (-1, C, H, 1, W, 1)).repeat(1, 1, 1, factor, 1, factor)
+    return torch.reshape(x, (-1, C, H * factor, W * factor))
+
+
+def naive_downsample_2d(x, factor=2):
+    _N, C, H, W = x.shape
+    return torch.mean(torch.reshape(x, (-1, C, H // factor, factor, W // factor, factor)), dim=(3, 5))

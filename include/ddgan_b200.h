@@ -82,9 +82,11 @@ int ddg_gn_prepare(const double* stats_a, int Ca, const double* stats_b, int Cb,
 /* FIR resampling on PNHWC with the AdaGN+SiLU prologue fused on load (layerspp.py:279-293): [1,3,3,1] (x) [1,3,3,1]
  * mode 1: up x2 (upsample_2d, up_or_down_sampling.py:200-228), mode 2: down x2 (downsample_2d, :231-261),
  * mode 3: pad (2,2) FIR (H -> H+1) written space-to-depth for the stride-2 conv of conv_downsample_2d (:149-183):
- *         out [N][Ho+3][Wo+3][4*C -> Cout_pitch], Ho = H/2, cell (i,j) channel (py*2+px)*C + c = fir[2i+py][2j+px][c]. */
+ *         out [N][Ho+3][Wo+3][4*C -> Cout_pitch], Ho = H/2, cell (i,j) channel (py*2+px)*C + c = fir[2i+py][2j+px][c].
+ * mode 4: adjoint of mode 3 (x is the space-to-depth gradient [N][H/2+3][W/2+3][in_pitch], out is [N][H+2][W+2][C]).
+ * gain multiplies the taps (the adjoint of up x2 is down x2 with gain 4, the adjoint of down x2 is up x2 with gain 1/4). */
 int ddg_fir_pnhwc(const float* x, const float* scale, const float* shift, int act, float* out, int N, int H, int W, int C,
-                  int mode, int out_pitch, double* stats, cudaStream_t stream);
+                  int mode, int out_pitch, float gain, cudaStream_t stream);
 /* minibatch stddev feature (discriminator.py:150-158) from a PNHWC tensor -> PNHWC [N][H+2][W+2][Cpad] channel 0 */
 int ddg_minibatch_stddev(const float* x, float* out, int N, int H, int W, int C, int Cpad, int group, cudaStream_t stream);
 /* out[n][c] = sum_{h,w} act(x[n][h][w][c]) over the interior of a PNHWC tensor (discriminator.py:163-165) */
@@ -142,6 +144,35 @@ int ddg_conv_pack_weights(const float* w, void* out, int cout, int cin_real, int
                           long s_tap, int flip_taps, int kb, int stage_offset, int total_stages, int precision, int batch,
                           long w_batch_stride, cudaStream_t stream);
 int ddg_conv2d_fwd(const ddg_conv_desc* desc, cudaStream_t stream);
+
+/* Weight gradient of the same convolution (cuDNN wgrad in the reference's backward, ddgan.py:459-506):
+ *   dw[co*s_co + ci*s_ci + tap*s_tap] += sum_q dy[q][co] * x[q + tap_dr*Wp + tap_ds][ci]   over the padded space [N][Hp][Wp]
+ * x: PNHWC source as seen by the conv (pitch xpitch, Cin_pad channels used, Cin_real scattered);
+ * dy: PNHWC output gradient with zero border (pitch dypitch, dy_cpad channels present).  dw must be zero-initialised
+ * by the caller (the kernel accumulates with fp32 reductions across its split-K CTAs). */
+typedef struct {
+  const float* x; const float* dy; float* dw;
+  int xpitch, dypitch;
+  int N, Hp, Wp;
+  int Cout, dy_cpad, Cin_real, Cin_pad;
+  int ntaps;
+  int8_t tap_dr[9]; int8_t tap_ds[9];
+  long s_co, s_ci, s_tap;
+  int precision;
+} ddg_wgrad_desc;
+int ddg_conv2d_wgrad(const ddg_wgrad_desc* desc, cudaStream_t stream);
+
+/* ---- PNHWC training helpers --------------------------------------------------------------------------------------
+ * y = act(scale[n,c] * x + shift[n,c]) on the interior (border stays zero): AdaGN / GN apply + SiLU (layerspp.py:279,300) */
+int ddg_affine_act_fwd(const float* x, const float* scale, const float* shift, float* y, int N, int H, int W, int C, int act,
+                       cudaStream_t stream);
+/* dx = dy * act'(u) * scale, sums[n][c] = {sum dy*act'(u)*x, sum dy*act'(u)} (float64, accumulated: zero it first) */
+int ddg_affine_act_bwd(const float* x, const float* dy, const float* scale, const float* shift, float* dx, double* sums, int N,
+                       int H, int W, int C, int act, cudaStream_t stream);
+/* stats[n][c] = {sum x, sum x^2} over the interior (float64, accumulated: zero it first) */
+int ddg_stats_fwd(const float* x, double* stats, int N, int H, int W, int C, cudaStream_t stream);
+/* dx = g1[n][c] + 2 * x * g2[n][c] on the interior, g = [N][C][2] float32 */
+int ddg_stats_bwd(const float* x, const float* g, float* dx, int N, int H, int W, int C, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,133 @@
+"""Training path on the GPU: gradient parity of the differentiable operators and of the full adversarial step
+(ddgan.py:443-518, incl. the R1 double-backward) against the CPU oracle / the reference's own gradients."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import ddgan_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+GTOL = 2e-4   # gradients accumulate several BF16x3 GEMMs; still well inside 1e-3
+
+
+def seeded(shape, seed, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+@pytest.mark.parametrize('n,cin,cout,h,k', [(2, 32, 64, 8, 3), (4, 64, 128, 16, 3), (3, 128, 32, 8, 1), (2, 256, 256, 4, 3), (8, 128, 128, 32, 3)])
+def test_conv_grads_and_double_backward(n, cin, cout, h, k):
+    from ddgan_b200 import train_graph as TG
+    x = seeded((n, cin, h, h), 1); w = seeded((cout, cin, k, k), 2) / math.sqrt(cin * k * k); b = seeded((cout,), 3, 0.1)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = F.conv2d(xr, wr, br, padding=k // 2)
+    gy = seeded(tuple(ref.shape), 4)
+    # first order + a double-backward scalar: s = sum(g_x^2) with g_x = d(sum(ref*gy))/dx
+    gx_ref, = torch.autograd.grad((ref * gy).sum(), xr, create_graph=True)
+    (gx_ref ** 2).sum().backward()
+    ggw_ref = wr.grad.clone()
+    wr.grad = None
+    gx1, gw1, gb1 = torch.autograd.grad((F.conv2d(xr, wr, br, padding=k // 2) * gy).sum(), (xr, wr, br))
+
+    xd = x.to(DEV).requires_grad_(True); wd = w.to(DEV).requires_grad_(True); bd = b.to(DEV).requires_grad_(True)
+    xp = TG.ToPnhwcFn.apply(xd, cin)
+    y = TG.conv3x3(xp, wd, bd, n, h, h) if k == 3 else TG.conv1x1(xp, wd, bd, n, h, h)
+    yo = TG.FromPnhwcFn.apply(y, cout)
+    assert O.rel_l2(yo.detach().cpu(), ref.detach()) < 2e-5
+    gx, gw, gb = torch.autograd.grad((yo * gy.to(DEV)).sum(), (xd, wd, bd), create_graph=True)
+    assert O.rel_l2(gx.detach().cpu(), gx1) < 5e-5
+    assert O.rel_l2(gw.detach().cpu(), gw1) < 5e-5
+    assert O.rel_l2(gb.detach().cpu(), gb1) < 5e-5
+    ggw, = torch.autograd.grad((gx ** 2).sum(), wd)
+    assert O.rel_l2(ggw.cpu(), ggw_ref) < GTOL
+
+
+def test_groupnorm_fir_linear_grads():
+    from ddgan_b200 import train_graph as TG
+    from ddgan_b200 import ops
+    n, c, h = 3, 64, 8
+    x = seeded((n, c, h, h), 5) * 1.5 + 0.3
+    gamma = 1 + seeded((n, c), 6) * 0.2; beta = seeded((n, c), 7) * 0.2
+    xr, gr, br = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = F.silu(gr[:, :, None, None] * O.group_norm(xr, O.num_groups(c)) + br[:, :, None, None])
+    ref = O.downsample_2d(O.upsample_2d(ref))
+    gy = seeded(tuple(ref.shape), 8)
+    g_ref = torch.autograd.grad((ref * gy).sum(), (xr, gr, br))
+    xd, gd, bd = x.to(DEV).requires_grad_(True), gamma.to(DEV).requires_grad_(True), beta.to(DEV).requires_grad_(True)
+    y = TG.group_norm_act(TG.ToPnhwcFn.apply(xd, c), h, h, O.num_groups(c), gd, bd, ops.ACT_SILU)
+    y = TG.fir_down(TG.fir_up(y))
+    yo = TG.FromPnhwcFn.apply(y, c)
+    assert O.rel_l2(yo.detach().cpu(), ref.detach()) < 1e-5
+    g = torch.autograd.grad((yo * gy.to(DEV)).sum(), (xd, gd, bd))
+    for a, b_ in zip(g, g_ref):
+        assert O.rel_l2(a.cpu(), b_) < 5e-5
+    # linear
+    xl = seeded((64, 100), 9); W = seeded((256, 100), 10, 0.1); b = seeded((256,), 11)
+    xr, Wr, br = xl.clone().requires_grad_(True), W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    gy = seeded((64, 256), 12)
+    g_ref = torch.autograd.grad((F.linear(xr, Wr, br) * gy).sum(), (xr, Wr, br))
+    xd, Wd, bd = xl.to(DEV).requires_grad_(True), W.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    g = torch.autograd.grad((TG.LinearFn.apply(xd, Wd, bd) * gy.to(DEV)).sum(), (xd, Wd, bd))
+    for a, b_ in zip(g, g_ref):
+        assert O.rel_l2(a.cpu(), b_) < 1e-5
+
+
+def _nets():
+    from ddgan_b200.modules import NCSNpp, Discriminator_small
+    cfg = O.tiny_config(image_size=32, attn_resolutions=(16,), t_emb_dim=32, ngf=16)
+    netG = NCSNpp(cfg).to(DEV)
+    netG.load_state_dict(O.randomize_params(O.ncsnpp_param_shapes(cfg), seed=21))
+    netD = Discriminator_small(nc=6, ngf=16, t_emb_dim=32).to(DEV)
+    netD.load_state_dict(O.randomize_params(O.discriminator_param_shapes(6, 16, 32), seed=22))
+    return cfg, netG, netD
+
+
+def test_adversarial_step_gradients_vs_reference(golden):
+    """The D step (real + R1 + fake, three backward calls accumulating into .grad) and the G step of ddgan.py:443-508 with the
+    reference's own gradients (tests/golden/make_golden.py) as the expected values."""
+    from ddgan_b200 import diffusion
+    g = golden['train_tiny']
+    cfg, netG, netD = _nets()
+    coeff = diffusion.DiffusionCoefficients(cfg, DEV); pc = diffusion.PosteriorCoefficients(cfg, DEV)
+    real = torch.tanh(seeded((4, 3, 32, 32), 300)).to(DEV); t = torch.tensor([0, 1, 2, 3], device=DEV)
+    n_xtp1, n_xt, n_post = (seeded((4, 3, 32, 32), s).to(DEV) for s in (301, 302, 303))
+    z = seeded((4, cfg.nz), 304).to(DEV)
+    x_t, x_tp1 = diffusion.q_sample_pairs(coeff, real, t, noise_xt=n_xt, noise_xtp1=n_xtp1)
+    x_t.requires_grad = True
+    netD.zero_grad(); netG.zero_grad()
+    D_real = netD(x_t, t, x_tp1.detach()).view(-1)
+    errD_real = F.softplus(-D_real).mean()
+    errD_real.backward(retain_graph=True)
+    grad_real = torch.autograd.grad(outputs=D_real.sum(), inputs=x_t, create_graph=True)[0]
+    gp = g['r1_gamma'] / 2 * (grad_real.view(grad_real.size(0), -1).norm(2, dim=1) ** 2).mean()
+    gp.backward()
+    x0p = netG(x_tp1.detach(), t, z)
+    x_pos = diffusion.sample_posterior(pc, x0p, x_tp1, t, noise=n_post)
+    output = netD(x_pos, t, x_tp1.detach()).view(-1)
+    errD_fake = F.softplus(output).mean()
+    errD_fake.backward()
+    assert abs(float(errD_real) - float(g['errD_real'])) < 1e-4 * max(1, abs(float(g['errD_real'])))
+    assert abs(float(gp) - float(g['gp'])) < 5e-4 * abs(float(g['gp']))
+    assert abs(float(errD_fake) - float(g['errD_fake'])) < 1e-4 * max(1, abs(float(g['errD_fake'])))
+    assert O.rel_l2(x_pos.detach().cpu(), g['x_pos']) < 1e-4
+    gd = dict(netD.named_parameters())
+    worst = max(O.rel_l2(gd[k].grad.cpu(), v) for k, v in g['gradD'].items())
+    assert worst < 5e-4, worst
+    gg = dict(netG.named_parameters())
+    worst = max(O.rel_l2(gg[k].grad.cpu(), v) for k, v in g['gradG_in_dstep'].items())
+    assert worst < 5e-4, worst
+    # G step
+    netG.zero_grad()
+    for p in netD.parameters():
+        p.requires_grad = False
+    x0p = netG(x_tp1.detach(), t, z)
+    x_pos = diffusion.sample_posterior(pc, x0p, x_tp1, t, noise=n_post)
+    errG = F.softplus(-netD(x_pos, t, x_tp1.detach()).view(-1)).mean()
+    errG.backward()
+    assert abs(float(errG) - float(g['errG'])) < 1e-4 * max(1, abs(float(g['errG'])))
+    worst = max(O.rel_l2(gg[k].grad.cpu(), v) for k, v in g['gradG'].items())
+    assert worst < 5e-4, worst
+    tot = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in netG.parameters()))
+    assert abs(float(tot) - float(g['gradG_norm'])) < 5e-4 * float(g['gradG_norm'])
