@@ -138,6 +138,154 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def cpu_baseline_train(batch, steps, warmup, threads=None):
+    """Reference train-step body (ddgan.py:443-518: D real + R1 + fake, G step; losses and all gradients) on the host CPU via
+    the oracle port; optimiser updates excluded (negligible next to the backward passes)."""
+    import torch
+    from oracle import ddgan_oracle as O
+    cfg = O.cifar10_config()
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    sd_g = {k: v.requires_grad_(True) for k, v in O.randomize_params(O.ncsnpp_param_shapes(cfg), seed=1).items()}
+    sd_d = {k: v.requires_grad_(True) for k, v in O.randomize_params(O.discriminator_param_shapes(6, 64, 256), seed=2).items()}
+    times = []
+    for i in range(warmup + steps):
+        real = torch.rand(batch, 3, 32, 32) * 2 - 1
+        t = torch.randint(0, 4, (batch,))
+        noises = [torch.randn(batch, 3, 32, 32) for _ in range(3)]
+        z = torch.randn(batch, cfg.nz)
+        t0 = time.perf_counter()
+        er, gp, ef = O.d_step_losses(sd_g, sd_d, cfg, real, t, noises, z, 0.02, do_r1=(i % 15 == 0))
+        (er + ef + (gp if gp is not None else 0.0)).backward()
+        for p_ in list(sd_g.values()) + list(sd_d.values()):
+            p_.grad = None
+        eg = O.g_step_loss(sd_g, {k: v.detach() for k, v in sd_d.items()}, cfg, real, t, noises, z)
+        eg.backward()
+        for p_ in sd_g.values():
+            p_.grad = None
+        times.append(time.perf_counter() - t0)
+    times = times[warmup:]
+    dt = sum(times) / len(times)
+    return batch / dt, dt, torch.get_num_threads()
+
+
+def train_args():
+    from ddgan_b200 import arch
+    cfg = arch.make_config()
+    # readme.md:31-37 CIFAR-10 command; betas = the fork's flag defaults (train_ddgan.py:86-89)
+    for k, v in dict(lr_g=1.6e-4, lr_d=1.25e-4, beta1=0.5, beta2=0.9, r1_gamma=0.02, lazy_reg=15, grad_clip_norm=1.0,
+                     ema_decay=0.9999, use_ema=True, batch_size=64).items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def run_b200_train(args):
+    import torch
+    import torch.distributed as dist
+    from ddgan_b200 import ops
+    from ddgan_b200.modules import NCSNpp, Discriminator_small
+    from ddgan_b200.train import Trainer
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    cfg = train_args()
+    B = args.batch
+    torch.manual_seed(1024 + rank)
+    netG = NCSNpp(cfg).to(dev)
+    netD = Discriminator_small(nc=2 * cfg.num_channels, ngf=cfg.ngf, t_emb_dim=cfg.t_emb_dim).to(dev)
+    netG.precision = netD.precision = args.precision
+    tr = Trainer(cfg, netG, netD, dev, distributed=world > 1)
+    real = (torch.rand(B, 3, 32, 32, device=dev) * 2 - 1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        tr.step(real, 0 if i == 0 else i)          # the first warm-up step exercises the R1 double-backward path
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        tr.step(real, i)                            # lazy R1 on steps 0, 15, 30, ... as in the reference
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    # end to end: host batch -> device every step, both losses read back (.item() as ddgan.py:480,510)
+    h_real = (torch.rand(B, 3, 32, 32) * 2 - 1).pin_memory()
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        errD, errG = tr.step(h_real.to(dev, non_blocking=True), i)
+        _ = errD.item(), errG.item()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    tt = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(tt[0]), float(tt[1])
+    if rank == 0:
+        # tensor-core kernel time inside one R1 step and one plain step (per-launch CUDA events on the launching stream)
+        ops.PROFILE['on'] = True
+        launches = {}
+        agg = {}
+        for gs in (15, 16):
+            ops.PROFILE['records'] = []
+            tr.step(real, gs)
+            torch.cuda.synchronize()
+            for name, fl, a, b in ops.PROFILE['records']:
+                e = agg.setdefault((gs, name), [0, 0.0, 0.0])
+                e[0] += 1; e[1] += fl; e[2] += a.elapsed_time(b)
+        ops.PROFILE['on'] = False
+        # weighted by the lazy_reg mix: 1 R1 step + 14 plain steps
+        def mix(name, idx):
+            return (agg.get((15, name), [0, 0, 0])[idx] + 14 * agg.get((16, name), [0, 0, 0])[idx]) / 15.0
+        conv_ms, conv_fl = mix('conv_tc', 2) + mix('wgrad_tc', 2), mix('conv_tc', 1) + mix('wgrad_tc', 1)
+        n_launch = mix('conv_tc', 0) + mix('wgrad_tc', 0)
+        pk, pk_kind = peaks()
+        peak = pk.get('bf16_tflops_sustained', pk['bf16_tflops'])
+        achieved = conv_fl / (conv_ms * 1e-3) / 1e12
+        samples = B * world * args.steps
+        value = samples / (ms * 1e-3)
+        line = {
+            'metric': 'cifar10_train_samples_per_sec', 'value': value, 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32 (BF16x3 split operands on tcgen05, fp32 accumulate)' if args.precision == 3 else 'bf16',
+            'data': 'synthetic',
+            'config': {'workload': 'cifar10_train_step_b64', 'model': 'NCSN++ ch128 1-2-2-2 nz100 + Discriminator_small ngf64',
+                       'T': 4, 'batch_per_gpu': B, 'r1_gamma': 0.02, 'lazy_reg': 15, 'optimizer': 'Adam lr_g 1.6e-4 lr_d 1.25e-4',
+                       'parallelism': f'data parallel x{world}: one flat NCCL all-reduce(mean) per network per step',
+                       'l2': 'activations saved for backward (~10 GB per step) exceed the 126 MB L2; no explicit flush'},
+            'e2e': {'value': samples / (ms_e2e * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': B * 3 * 32 * 32 * 4, 'd2h_bytes_per_step': 8},
+            'gpu_launches': int(n_launch * args.steps),
+            'clocks': clk,
+            'roofline': {'bound': 'tensor', 'kernel': 'conv_tc_kernel + wgrad_tc_kernel (fwd, dgrad, wgrad; lazy-R1 mix 1:14)',
+                         'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+                         'peak_source': f'{pk_kind} bf16_tflops_sustained', 'tc_ms_per_step': conv_ms, 'tc_flops_per_step': conv_fl,
+                         'tc_launches_per_step': n_launch,
+                         'note': 'algorithmic FLOPs of the launched GEMMs (padded channels included); BF16x3 issues 3 MMAs per MAC'},
+            'model_tflops': 108e9 * value / 1e12,
+        }
+        if not args.skip_cpu_baseline:
+            sps, dt, th = cpu_baseline_train(4, 1, 1)
+            line['cpu_baseline'] = {'value': sps, 'unit': 'samples/s', 'cores': th, 'kind': 'port',
+                                    'sample': f'1 train step (D real + fake, G; no R1) at batch 4 after 1 warm-up step with R1, {th} threads'}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -280,6 +428,8 @@ def main():
     args = parse()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload == 'train':
+        run_b200_train(args)
     else:
         run_b200(args)
 

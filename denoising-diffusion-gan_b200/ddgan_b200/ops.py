@@ -246,6 +246,13 @@ def conv_wgrad(x, dy, dw, n, hp, wp, cout, cin_real, cin_pad, taps, s_co, s_ci, 
         d.tap_dr[t] = dr; d.tap_ds[t] = ds
     d.s_co, d.s_ci, d.s_tap = s_co, s_ci, s_tap
     d.precision = precision
+    if PROFILE['on']:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        check(lib().ddg_conv2d_wgrad(C.byref(d), stream()), 'conv2d_wgrad')
+        b.record()
+        PROFILE['records'].append(('wgrad_tc', 2.0 * n * (hp - 2) * (wp - 2) * cout * cin_pad * len(taps), a, b))
+        return dw
     check(lib().ddg_conv2d_wgrad(C.byref(d), stream()), 'conv2d_wgrad')
     return dw
 
@@ -351,7 +358,23 @@ def build_conv_desc(weights: ConvWeights, srcs, n, hout, wout, out, out_mode=OUT
     return d
 
 
+# Optional per-launch timing of the tensor-core kernels (bench.py roofline): CUDA events on the launching stream.
+PROFILE = {'on': False, 'records': []}
+
+
+def _conv_flops(d: ConvDesc):
+    k = sum(d.src[i].C * d.src[i].ntaps for i in range(d.nsrc))
+    return 2.0 * d.N * d.Hout * d.Wout * d.Cout * k
+
+
 def conv_launch(desc: ConvDesc):
+    if PROFILE['on']:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        check(lib().ddg_conv2d_fwd(C.byref(desc), stream()), 'conv2d_fwd')
+        b.record()
+        PROFILE['records'].append(('conv_tc', _conv_flops(desc), a, b))
+        return
     check(lib().ddg_conv2d_fwd(C.byref(desc), stream()), 'conv2d_fwd')
 
 

@@ -1,0 +1,166 @@
+"""The adversarial training step of DDGAN (ddgan.py:443-518) and its data-parallel glue (ddgan.py:30-33, 292-294, 363-365).
+
+`Trainer.step(real, global_step)` is the loop body of the reference: D step (real, lazy R1 every `lazy_reg`, fake), clip,
+Adam; G step, clip, Adam; EMA.  Data parallelism follows the rule SURVEY.md section 2.4 established empirically for the
+reference's DDP: every rank accumulates all of a network's gradient contributions locally and ONE all-reduce(mean) per
+network per step makes them identical on all ranks -- implemented here as a single flat-buffer NCCL all-reduce per network
+(`FlatGradAllReducer`) instead of DDP's per-bucket hooks around three `backward()` calls."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import diffusion
+
+
+def broadcast_params(params, src=0):
+    """ddgan.py:30-33."""
+    for p in params:
+        dist.broadcast(p.data, src=src)
+
+
+class FlatGradAllReducer:
+    """All-reduce(mean) of the accumulated .grad of a parameter list through one flat buffer (one collective per call)."""
+
+    def __init__(self, params, world_size=None, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.world = world_size if world_size is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+        n = sum(p.numel() for p in self.params)
+        p0 = self.params[0]
+        self.flat = torch.zeros(n, device=p0.device, dtype=p0.dtype)
+        self.views = []
+        off = 0
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    def allreduce(self):
+        if self.world <= 1:
+            return
+        with torch.no_grad():
+            for v, p in zip(self.views, self.params):
+                if p.grad is None:
+                    v.zero_()
+                else:
+                    v.copy_(p.grad)
+            dist.all_reduce(self.flat, group=self.group)
+            self.flat.div_(self.world)
+            for v, p in zip(self.views, self.params):
+                if p.grad is None:
+                    p.grad = v.clone()
+                else:
+                    p.grad.copy_(v)
+
+
+class EMA:
+    """ema.py:45-55: ema = decay * ema + (1 - decay) * param, per parameter (multi-tensor ops)."""
+
+    def __init__(self, model, ema_decay=0.999):
+        self.decay = ema_decay
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.names = [n for n, p in model.named_parameters() if p.requires_grad]
+        self.shadow = [p.detach().clone() for p in self.params]
+
+    @torch.no_grad()
+    def step(self):
+        if self.decay <= 0:
+            return
+        torch._foreach_mul_(self.shadow, self.decay)
+        torch._foreach_add_(self.shadow, [p.detach() for p in self.params], alpha=1.0 - self.decay)
+
+    def state_dict(self):
+        return {n: s.cpu() for n, s in zip(self.names, self.shadow)}
+
+    @torch.no_grad()
+    def swap_parameters_with_ema(self, store_params_in_ema=True):
+        for p, s in zip(self.params, self.shadow):
+            if store_params_in_ema:
+                tmp = p.detach().clone()
+                p.data.copy_(s)
+                s.copy_(tmp)
+            else:
+                p.data.copy_(s)
+
+
+class Trainer:
+    """args needs: num_timesteps, beta_min, beta_max, use_geometric, nz, lr_g, lr_d, beta1, beta2, r1_gamma, lazy_reg,
+    grad_clip_norm, ema_decay (names as in train_ddgan.py)."""
+
+    def __init__(self, args, netG, netD, device, distributed=False):
+        self.args = args
+        self.netG, self.netD = netG, netD
+        self.dev = device
+        self.coeff = diffusion.DiffusionCoefficients(args, device)
+        self.pos_coeff = diffusion.PosteriorCoefficients(args, device)
+        betas = (getattr(args, 'beta1', 0.5), getattr(args, 'beta2', 0.9))
+        self.optD = torch.optim.Adam(netD.parameters(), lr=args.lr_d, betas=betas)
+        self.optG = torch.optim.Adam(netG.parameters(), lr=args.lr_g, betas=betas)
+        self.ema = EMA(netG, getattr(args, 'ema_decay', 0.9999)) if getattr(args, 'use_ema', True) else None
+        self.distributed = distributed and dist.is_initialized() and dist.get_world_size() > 1
+        if self.distributed:
+            broadcast_params(netG.parameters())
+            broadcast_params(netD.parameters())
+            self.arG = FlatGradAllReducer(netG.parameters())
+            self.arD = FlatGradAllReducer(netD.parameters())
+
+    def step(self, real_data, global_step, noise=None):
+        """One iteration of ddgan.py:443-518.  `noise` (parity runs) = dict with t_d, n_xtp1_d, n_xt_d, z_d, n_post_d and the
+        same with suffix _g; by default everything is drawn with torch's CUDA generator in the reference's order."""
+        a, netG, netD = self.args, self.netG, self.netD
+        nz = noise or {}
+        B = real_data.size(0)
+        # ---------------- D step ----------------
+        for p in netD.parameters():
+            p.requires_grad = True
+        netD.zero_grad(set_to_none=True)
+        t = nz.get('t_d', None)
+        if t is None:
+            t = torch.randint(0, a.num_timesteps, (B,), device=self.dev)
+        x_t, x_tp1 = diffusion.q_sample_pairs(self.coeff, real_data, t, noise_xt=nz.get('n_xt_d'), noise_xtp1=nz.get('n_xtp1_d'))
+        x_t.requires_grad = True
+        D_real = netD(x_t, t, x_tp1.detach()).view(-1)
+        errD_real = F.softplus(-D_real).mean()
+        do_r1 = (a.lazy_reg is None) or (global_step % a.lazy_reg == 0)
+        errD_real.backward(retain_graph=do_r1)
+        if do_r1:
+            grad_real = torch.autograd.grad(outputs=D_real.sum(), inputs=x_t, create_graph=True)[0]
+            grad_penalty = a.r1_gamma / 2 * (grad_real.view(B, -1).norm(2, dim=1) ** 2).mean()
+            grad_penalty.backward()
+        z = nz.get('z_d')
+        if z is None:
+            z = torch.randn(B, a.nz, device=self.dev)
+        x_0_predict = netG(x_tp1.detach(), t, z)
+        x_pos_sample = diffusion.sample_posterior(self.pos_coeff, x_0_predict, x_tp1, t, noise=nz.get('n_post_d'))
+        output = netD(x_pos_sample, t, x_tp1.detach()).view(-1)
+        errD_fake = F.softplus(output).mean()
+        errD_fake.backward()
+        errD = errD_real.detach() + errD_fake.detach()
+        if self.distributed:
+            self.arD.allreduce()
+        torch.nn.utils.clip_grad_norm_(netD.parameters(), max_norm=a.grad_clip_norm)
+        self.optD.step()
+        # ---------------- G step ----------------
+        for p in netD.parameters():
+            p.requires_grad = False
+        netG.zero_grad(set_to_none=True)
+        t = nz.get('t_g', None)
+        if t is None:
+            t = torch.randint(0, a.num_timesteps, (B,), device=self.dev)
+        x_t, x_tp1 = diffusion.q_sample_pairs(self.coeff, real_data, t, noise_xt=nz.get('n_xt_g'), noise_xtp1=nz.get('n_xtp1_g'))
+        z = nz.get('z_g')
+        if z is None:
+            z = torch.randn(B, a.nz, device=self.dev)
+        x_0_predict = netG(x_tp1.detach(), t, z)
+        x_pos_sample = diffusion.sample_posterior(self.pos_coeff, x_0_predict, x_tp1, t, noise=nz.get('n_post_g'))
+        output = netD(x_pos_sample, t, x_tp1.detach()).view(-1)
+        errG = F.softplus(-output).mean()
+        errG.backward()
+        if self.distributed:
+            self.arG.allreduce()
+        torch.nn.utils.clip_grad_norm_(netG.parameters(), max_norm=a.grad_clip_norm)
+        self.optG.step()
+        if self.ema is not None:
+            self.ema.step()
+        return errD, errG.detach()
