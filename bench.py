@@ -7,7 +7,8 @@
 Workload `cifar10_sample_T4_b64`: BASELINE.json configs[0] -- CIFAR-10 NCSN++ (ch 128, ch_mult 1-2-2-2, nz 100), T = 4
 posterior-sampling steps, 64 images per GPU per step, random-init-shaped (re-randomised) weights, synthetic noise.
 One "step" = one full sampling pass (4 generator forwards + 4 posterior updates) over one batch of 64 images per GPU.
-`--workload train` times the adversarial train step instead (configs[1]) once it is enabled.
+The default run (`--workload both`) also times the adversarial train step (configs[1]: G + Discriminator_small fwd/bwd, lazy R1,
+Adam, EMA at batch 64/GPU) and reports it under the key `train` of the same JSON line; `--workload train` prints it alone.
 """
 import argparse
 import json
@@ -32,7 +33,8 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='sample', choices=['sample', 'train'])
+    ap.add_argument('--workload', default='both', choices=['both', 'sample', 'train'],
+                    help="'both' (default): sampling line with the train-step results under key 'train'")
     ap.add_argument('--batch', type=int, default=64, help='images per GPU per step')
     ap.add_argument('--precision', type=int, default=3, help='3 = BF16x3 (fp32 parity mode, headline), 1 = BF16')
     ap.add_argument('--no-graph', action='store_true')
@@ -135,6 +137,11 @@ def run_reference(args):
         'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
+    if args.workload in ('both', 'train'):
+        sps, dt2, th2 = cpu_baseline_train(4, 1, 1)
+        line['train'] = {'metric': 'cifar10_train_samples_per_sec', 'value': sps, 'unit': 'samples/s', 'ms_per_step': dt2 * 1e3,
+                         'cpu_baseline': {'value': sps, 'unit': 'samples/s', 'cores': th2, 'kind': 'port',
+                                          'sample': '1 train step (D real + fake, G; no R1) at batch 4 after a warm-up step with R1'}}
     print(json.dumps(line), flush=True)
 
 
@@ -179,7 +186,7 @@ def train_args():
     return cfg
 
 
-def run_b200_train(args):
+def run_b200_train(args, emit=True):
     import torch
     import torch.distributed as dist
     from ddgan_b200 import ops
@@ -190,7 +197,7 @@ def run_b200_train(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group('nccl', device_id=dev)
     cfg = train_args()
     B = args.batch
@@ -234,19 +241,21 @@ def run_b200_train(args):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(tt[0]), float(tt[1])
+    # tensor-core kernel time inside one R1 step and one plain step (per-launch CUDA events on the launching stream).
+    # Every rank runs these two steps (they contain the gradient all-reduce); only rank 0 reports.
+    ops.PROFILE['on'] = True
+    agg = {}
+    for gs in (15, 16):
+        ops.PROFILE['records'] = []
+        tr.step(real, gs)
+        torch.cuda.synchronize()
+        for name, fl, a, b in ops.PROFILE['records']:
+            e = agg.setdefault((gs, name), [0, 0.0, 0.0])
+            e[0] += 1; e[1] += fl; e[2] += a.elapsed_time(b)
+    ops.PROFILE['on'] = False
+    barrier()
+    line = None
     if rank == 0:
-        # tensor-core kernel time inside one R1 step and one plain step (per-launch CUDA events on the launching stream)
-        ops.PROFILE['on'] = True
-        launches = {}
-        agg = {}
-        for gs in (15, 16):
-            ops.PROFILE['records'] = []
-            tr.step(real, gs)
-            torch.cuda.synchronize()
-            for name, fl, a, b in ops.PROFILE['records']:
-                e = agg.setdefault((gs, name), [0, 0.0, 0.0])
-                e[0] += 1; e[1] += fl; e[2] += a.elapsed_time(b)
-        ops.PROFILE['on'] = False
         # weighted by the lazy_reg mix: 1 R1 step + 14 plain steps
         def mix(name, idx):
             return (agg.get((15, name), [0, 0, 0])[idx] + 14 * agg.get((16, name), [0, 0, 0])[idx]) / 15.0
@@ -280,10 +289,12 @@ def run_b200_train(args):
             sps, dt, th = cpu_baseline_train(4, 1, 1)
             line['cpu_baseline'] = {'value': sps, 'unit': 'samples/s', 'cores': th, 'kind': 'port',
                                     'sample': f'1 train step (D real + fake, G; no R1) at batch 4 after 1 warm-up step with R1, {th} threads'}
-        print(json.dumps(line), flush=True)
-    if world > 1:
+        if emit:
+            print(json.dumps(line), flush=True)
+    if world > 1 and emit:
         dist.barrier()
         dist.destroy_process_group()
+    return line
 
 
 def run_b200(args):
@@ -329,6 +340,7 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    line = None
     # ---- device-resident throughput ----
     for _ in range(max(args.warmup, 3)):
         smp.sample(x_init)
@@ -418,6 +430,15 @@ def run_b200(args):
             ips, dt, th = cpu_baseline_sampling(args.cpu_sample_batch, 1, 1)
             line['cpu_baseline'] = {'value': ips, 'unit': 'images/s', 'cores': th, 'kind': 'port',
                                     'sample': f'1 x T=4 sampling of {args.cpu_sample_batch} images (after 1 warm-up), {th} threads'}
+    if args.workload == 'both':
+        del smp, eng
+        torch.cuda.empty_cache()
+        targs = argparse.Namespace(**vars(args))
+        targs.steps = max(15, min(args.steps, 30))
+        tl = run_b200_train(targs, emit=False)
+        if rank == 0:
+            line['train'] = tl
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
