@@ -95,8 +95,11 @@ class Trainer:
         self.coeff = diffusion.DiffusionCoefficients(args, device)
         self.pos_coeff = diffusion.PosteriorCoefficients(args, device)
         betas = (getattr(args, 'beta1', 0.5), getattr(args, 'beta2', 0.9))
-        self.optD = torch.optim.Adam(netD.parameters(), lr=args.lr_d, betas=betas)
-        self.optG = torch.optim.Adam(netG.parameters(), lr=args.lr_g, betas=betas)
+        # capturable=True keeps the Adam step counters on the device so that the whole step can be a CUDA graph
+        cap = torch.device(device).type == 'cuda'
+        self.optD = torch.optim.Adam(netD.parameters(), lr=args.lr_d, betas=betas, capturable=cap, foreach=True)
+        self.optG = torch.optim.Adam(netG.parameters(), lr=args.lr_g, betas=betas, capturable=cap, foreach=True)
+        self._graphs = None
         self.ema = EMA(netG, getattr(args, 'ema_decay', 0.9999)) if getattr(args, 'use_ema', True) else None
         self.distributed = distributed and dist.is_initialized() and dist.get_world_size() > 1
         if self.distributed:
@@ -114,7 +117,7 @@ class Trainer:
         # ---------------- D step ----------------
         for p in netD.parameters():
             p.requires_grad = True
-        netD.zero_grad(set_to_none=True)
+        netD.zero_grad(set_to_none=False)   # grads stay allocated (outside any CUDA-graph pool) and are zeroed in place
         t = nz.get('t_d', None)
         if t is None:
             t = torch.randint(0, a.num_timesteps, (B,), device=self.dev)
@@ -144,7 +147,7 @@ class Trainer:
         # ---------------- G step ----------------
         for p in netD.parameters():
             p.requires_grad = False
-        netG.zero_grad(set_to_none=True)
+        netG.zero_grad(set_to_none=False)
         t = nz.get('t_g', None)
         if t is None:
             t = torch.randint(0, a.num_timesteps, (B,), device=self.dev)
@@ -164,3 +167,42 @@ class Trainer:
         if self.ema is not None:
             self.ema.step()
         return errD, errG.detach()
+
+    # ------------------------------------------------------------------------------------------------------------
+    # whole-step CUDA graphs: the step is ~15 K kernel launches (launch-bound when issued from Python); captured once per
+    # variant (with / without the lazy R1 double-backward) it replays as two graph launches per iteration.
+    # ------------------------------------------------------------------------------------------------------------
+    def capture(self, batch_shape, warmup=3, variants=('r1', 'plain'), share_pool=False):
+        dev = self.dev
+        self.real_static = torch.zeros(batch_shape, device=dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for i in range(warmup):
+                self.step(self.real_static, 0 if i == 0 else 1)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self._graphs = {}
+        pool = None
+        for key, gs in (('r1', 0), ('plain', 1)):
+            if key not in variants:
+                continue
+            g = torch.cuda.CUDAGraph()
+            # separate pools by default: the two variants are replayed in data-dependent order (1 : lazy_reg-1), which a shared
+            # pool does not allow
+            with torch.cuda.graph(g, pool=pool if share_pool else None):
+                out = self.step(self.real_static, gs)
+            pool = g.pool()
+            self._graphs[key] = (g, out)
+        return self
+
+    def step_graphed(self, real_data, global_step):
+        """Same semantics as step() (fresh randomness every replay through the graph-safe CUDA generator)."""
+        if self._graphs is None:
+            raise RuntimeError('call capture(batch_shape) first')
+        a = self.args
+        do_r1 = (a.lazy_reg is None) or (global_step % a.lazy_reg == 0)
+        self.real_static.copy_(real_data, non_blocking=True)
+        g, out = self._graphs['r1' if do_r1 else 'plain']
+        g.replay()
+        return out
