@@ -709,11 +709,16 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
 // ---------------------------------------------------------------------------------------------------------
 struct Variant { int msub, nt, kb; };
 
-static int pick_nt(int cout) {
+static int g_nt256 = 1;  // N = 256 tiles for Cout % 256 == 0 (96 B/clk of operand reads per MMA instead of 128 B/clk at N = 128)
+
+// Output-channel tile.  N = 256 only when the grid still covers the machine (one wave of 128-row tiles at least).
+static int pick_nt(int cout, long m_rows) {
   if (cout <= 16) return 16;
   if (cout <= 64) return 64;
+  if (g_nt256 && cout % 256 == 0 && ((m_rows + 127) / 128) * (cout / 256) >= 148) return 256;
   return 128;
 }
+static bool valid_nt(int nt) { return nt == 16 || nt == 64 || nt == 128 || nt == 256; }
 
 template <int MSUB, int NT, int KB, int PREC>
 static int launch_conv(const ConvDev& d, int n_tiles, cudaStream_t stream) {
@@ -737,25 +742,25 @@ static int launch_conv(const ConvDev& d, int n_tiles, cudaStream_t stream) {
 
 using namespace ddg;
 
-extern "C" int ddg_conv_tile_n(int cout) { return pick_nt(cout); }
+extern "C" int ddg_conv_tile_n(int cout, long m_rows) { return pick_nt(cout, m_rows); }
+extern "C" int ddg_conv_set_nt256(int on) { const int old = g_nt256; g_nt256 = on ? 1 : 0; return old; }
 
-extern "C" long ddg_conv_packed_bytes(int cout, int total_stages, int kb, int precision) {
-  const int nt = pick_nt(cout);
+extern "C" long ddg_conv_packed_bytes(int cout, int total_stages, int kb, int precision, int nt) {
+  if (!valid_nt(nt)) return -1;
   const int n_tiles = (cout + nt - 1) / nt;
   return (long)n_tiles * total_stages * kb * nt * 2 * (precision == 3 ? 2 : 1);
 }
 
 extern "C" int ddg_conv_pack_weights(const float* w, void* out, int cout, int cin_real, int cin_pad, int ntaps, long s_co,
                                      long s_ci, long s_tap, int flip_taps, int kb, int stage_offset, int total_stages,
-                                     int precision, int batch, long w_batch_stride, cudaStream_t stream) {
-  if (!w || !out || cin_pad % kb != 0 || (kb != 32 && kb != 64)) { ddg_set_last_error("pack_weights: bad args"); return DDG_ERR_ARG; }
-  const int nt = pick_nt(cout);
+                                     int precision, int nt, int batch, long w_batch_stride, cudaStream_t stream) {
+  if (!w || !out || cin_pad % kb != 0 || (kb != 32 && kb != 64) || !valid_nt(nt)) { ddg_set_last_error("pack_weights: bad args"); return DDG_ERR_ARG; }
   const int n_tiles = (cout + nt - 1) / nt;
   const long total = (long)n_tiles * (cin_pad / kb) * ntaps * (kb / 8) * nt;
   const int threads = 256;
   const int blocks = (int)((total + threads - 1) / threads < 148 * 16 ? (total + threads - 1) / threads : 148 * 16);
   if (batch < 1) batch = 1;
-  const long out_bs = ddg_conv_packed_bytes(cout, total_stages, kb, precision) / 2;  // in bf16 elements
+  const long out_bs = ddg_conv_packed_bytes(cout, total_stages, kb, precision, nt) / 2;  // in bf16 elements
   dim3 grid(blocks, batch);
   if (precision == 3)
     pack_weights_kernel<3><<<grid, threads, 0, stream>>>(w, (__nv_bfloat16*)out, cout, cin_real, cin_pad, ntaps, s_co, s_ci,
@@ -822,18 +827,19 @@ extern "C" int ddg_conv2d_fwd(const ddg_conv_desc* c, cudaStream_t stream) {
   if (c->batch_rows > 0) {
     if (window || d.Mtotal % c->batch_rows != 0) { ddg_set_last_error("conv2d_fwd: batched mode needs a 1x1 problem with Mtotal % batch_rows == 0"); return DDG_ERR_ARG; }
     d.batch_rows = c->batch_rows;
-    d.w_batch_stride = ddg_conv_packed_bytes(c->Cout, total_stages, KB, c->precision == 1 ? 1 : 3);
+    d.w_batch_stride = ddg_conv_packed_bytes(c->Cout, total_stages, KB, c->precision == 1 ? 1 : 3, c->nt);
   }
   if (d.out_mode != 2 && (d.out_C % 4 != 0)) { ddg_set_last_error("conv2d_fwd: NHWC output pitch must be a multiple of 4"); return DDG_ERR_ARG; }
 
-  const int nt = pick_nt(c->Cout);
+  const int nt = c->nt;
+  if (!valid_nt(nt)) { ddg_set_last_error("conv2d_fwd: desc.nt must be the tile width the weights were packed with (16/64/128/256)"); return DDG_ERR_ARG; }
   const int n_tiles = (c->Cout + nt - 1) / nt;
   if (d.out_mode != 2 && (c->Cout % (nt >= 64 ? 32 : 16) != 0)) { ddg_set_last_error("conv2d_fwd: Cout must be a multiple of the epilogue chunk for NHWC output"); return DDG_ERR_UNSUPPORTED; }
   // M sub-tiles: two accumulators per CTA when the grid still fills the machine
   int msub = c->msub;
   if (msub == 0) {
     const long tiles2 = ((long)d.Mtotal + 255) / 256 * n_tiles;
-    msub = (tiles2 >= 2 * 148) ? 2 : 1;
+    msub = (tiles2 >= 222) ? 2 : 1;   // >= 1.5 waves of 256-row tiles
     if (d.batch_rows > 0 && d.batch_rows % 256 != 0) msub = 1;
   }
   const int MT = 128 * msub;
@@ -845,10 +851,12 @@ extern "C" int ddg_conv2d_fwd(const ddg_conv_desc* c, cudaStream_t stream) {
 
 #define DDG_LAUNCH(MS, NTV, PR) return launch_conv<MS, NTV, 32, PR>(d, n_tiles, stream)
   if (prec == 3) {
+    if (nt == 256) { if (msub == 2) DDG_LAUNCH(2, 256, 3); else DDG_LAUNCH(1, 256, 3); }
     if (nt == 128) { if (msub == 2) DDG_LAUNCH(2, 128, 3); else DDG_LAUNCH(1, 128, 3); }
     if (nt == 64) { if (msub == 2) DDG_LAUNCH(2, 64, 3); else DDG_LAUNCH(1, 64, 3); }
     if (nt == 16) { if (msub == 2) DDG_LAUNCH(2, 16, 3); else DDG_LAUNCH(1, 16, 3); }
   } else {
+    if (nt == 256) { if (msub == 2) DDG_LAUNCH(2, 256, 1); else DDG_LAUNCH(1, 256, 1); }
     if (nt == 128) { if (msub == 2) DDG_LAUNCH(2, 128, 1); else DDG_LAUNCH(1, 128, 1); }
     if (nt == 64) { if (msub == 2) DDG_LAUNCH(2, 64, 1); else DDG_LAUNCH(1, 64, 1); }
     if (nt == 16) { if (msub == 2) DDG_LAUNCH(2, 16, 1); else DDG_LAUNCH(1, 16, 1); }

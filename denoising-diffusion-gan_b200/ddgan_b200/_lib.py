@@ -22,7 +22,7 @@ class ConvSrc(C.Structure):
 
 
 class ConvDesc(C.Structure):
-    _fields_ = [('src', ConvSrc * MAX_SRC), ('nsrc', C.c_int), ('wpack', C.c_void_p), ('kb', C.c_int), ('N', C.c_int),
+    _fields_ = [('src', ConvSrc * MAX_SRC), ('nsrc', C.c_int), ('wpack', C.c_void_p), ('kb', C.c_int), ('nt', C.c_int), ('N', C.c_int),
                 ('Hout', C.c_int), ('Wout', C.c_int), ('Hp', C.c_int), ('Wp', C.c_int), ('Cout', C.c_int),
                 ('bias', C.c_void_p), ('addvec', C.c_void_p), ('addvec_stride', C.c_int), ('res', C.c_void_p),
                 ('out_scale', C.c_float), ('out_act', C.c_int), ('out', C.c_void_p), ('out_mode', C.c_int),
@@ -58,9 +58,10 @@ _SIGNATURES = {
     'ddg_minibatch_stddev': ([_P, _P] + [_I] * 6 + [_P], _I),
     'ddg_spatial_sum': ([_P, _P] + [_I] * 5 + [_P], _I),
     'ddg_softmax_rows': ([_P, _P, _L, _I, _I, _I, _P], _I),
-    'ddg_conv_tile_n': ([_I], _I),
-    'ddg_conv_packed_bytes': ([_I, _I, _I, _I], _L),
-    'ddg_conv_pack_weights': ([_P, _P, _I, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _I, _I, _L, _P], _I),
+    'ddg_conv_tile_n': ([_I, _L], _I),
+    'ddg_conv_set_nt256': ([_I], _I),
+    'ddg_conv_packed_bytes': ([_I, _I, _I, _I, _I], _L),
+    'ddg_conv_pack_weights': ([_P, _P, _I, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _L, _P], _I),
     'ddg_conv2d_fwd': ([C.POINTER(ConvDesc), _P], _I),
     'ddg_conv2d_wgrad': ([C.POINTER(WgradDesc), _P], _I),
     'ddg_affine_act_fwd': ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),

@@ -76,8 +76,10 @@ class _EngineBase:
 
     def _conv(self, cout, srcs, hout, wout, out, binder, **kw):
         """srcs: ops.conv_src dicts; binder(cw) packs the B operand from self.P.  Appends one launch."""
-        cw = ops.ConvWeights(cout, [(s['C'], len(s['taps'])) for s in srcs], self.dev, precision=self.prec)
         n = kw.pop('n', self.N)
+        window = any(len(s_['taps']) > 1 for s_ in srcs)
+        m_rows = n * kw.get('hp', hout + 2) * kw.get('wp', wout + 2) if window else n * hout * wout
+        cw = ops.ConvWeights(cout, [(s['C'], len(s['taps'])) for s in srcs], self.dev, precision=self.prec, m_rows=m_rows)
         desc = ops.build_conv_desc(cw, srcs, n, hout, wout, out, **kw)
         self._keep.append((cw, desc, srcs, kw, out))
         if binder is not None:

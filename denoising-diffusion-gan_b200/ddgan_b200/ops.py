@@ -284,13 +284,15 @@ class ConvWeights:
 
     segs: list of (C_padded, ntaps).  Call pack_segment() for each segment whenever the fp32 weights change."""
 
-    def __init__(self, cout: int, segs, device, precision: int = 3, batch: int = 1):
+    def __init__(self, cout: int, segs, device, precision: int = 3, batch: int = 1, m_rows: int = 0):
+        """m_rows: GEMM rows of the conv that will consume these weights (picks the output-channel tile width)."""
         self.cout = cout
+        self.nt = lib().ddg_conv_tile_n(cout, m_rows)
         self.segs = list(segs)
         self.precision = precision
         self.batch = batch
         self.total_stages = sum((c // KB) * nt for c, nt in self.segs)
-        self.bytes_per_batch = lib().ddg_conv_packed_bytes(cout, self.total_stages, KB, precision)
+        self.bytes_per_batch = lib().ddg_conv_packed_bytes(cout, self.total_stages, KB, precision, self.nt)
         self.buf = torch.empty(self.bytes_per_batch * batch, dtype=torch.uint8, device=device)
         self.offsets = []
         off = 0
@@ -304,7 +306,7 @@ class ConvWeights:
         require_cuda_f32(w)
         c, nt = self.segs[i]
         check(lib().ddg_conv_pack_weights(w.data_ptr() + 4 * elem_offset, ptr(self.buf), self.cout, cin_real, c, nt, s_co, s_ci, s_tap, int(flip),
-                                          KB, self.offsets[i], self.total_stages, self.precision, self.batch, w_batch_stride,
+                                          KB, self.offsets[i], self.total_stages, self.precision, self.nt, self.batch, w_batch_stride,
                                           stream()), 'conv_pack_weights')
 
     def pack_conv_weight(self, i: int, w: torch.Tensor):
@@ -343,6 +345,7 @@ def build_conv_desc(weights: ConvWeights, srcs, n, hout, wout, out, out_mode=OUT
         assert (s['C'], len(s['taps'])) == tuple(weights.segs[i]), 'source / packed-weight segment mismatch'
     d.wpack = ptr(weights.buf)
     d.kb = KB
+    d.nt = weights.nt
     d.N, d.Hout, d.Wout = n, hout, wout
     d.Hp = hp if hp is not None else hout + 2
     d.Wp = wp if wp is not None else wout + 2

@@ -64,7 +64,8 @@ def conv_spec(w_shape, taps, n, hout, wout, cpad_in, s_co, s_ci, s_tap, cout, ci
 
 
 def _conv_forward(x, w, bias, addvec, sp):
-    cw = ops.ConvWeights(sp.cout, [(sp.cpad_in, len(sp.taps))], x.device, precision=sp.prec)
+    m_rows = sp.n * sp.hp * sp.wp if len(sp.taps) > 1 else sp.n * sp.hout * sp.wout
+    cw = ops.ConvWeights(sp.cout, [(sp.cpad_in, len(sp.taps))], x.device, precision=sp.prec, m_rows=m_rows)
     cw.pack_segment(0, w, sp.cin, sp.s_co, sp.s_ci, sp.s_tap)
     if sp.out_nchw:
         out = torch.zeros(sp.n, sp.cout, sp.hout, sp.wout, device=x.device)
@@ -126,7 +127,8 @@ class DgradFn(Function):
         # output space = the conv's input space (hp x wp padded); dy is embedded into it when the spaces differ (2x2-tap conv)
         dye = _embed(dy, sp.hp, sp.wp).contiguous()
         cy = dye.shape[-1]
-        cw = ops.ConvWeights(sp.cpad_in, [(cy, len(sp.taps))], dy.device, precision=sp.prec)
+        m_rows = sp.n * sp.hp * sp.wp if len(sp.taps) > 1 else sp.n * (sp.hp - 2) * (sp.wp - 2)
+        cw = ops.ConvWeights(sp.cpad_in, [(cy, len(sp.taps))], dy.device, precision=sp.prec, m_rows=m_rows)
         cw.pack_segment(0, w, sp.cout, sp.s_ci, sp.s_co, sp.s_tap)   # roles of co / ci swapped
         dx = ops.alloc_pnhwc(sp.n, sp.hp - 2, sp.wp - 2, sp.cpad_in, dy.device)
         taps = [(-dr, -ds) for dr, ds in sp.taps]

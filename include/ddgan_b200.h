@@ -116,6 +116,7 @@ typedef struct {
   int nsrc;
   const void* wpack;   /* ddg_conv_pack_weights output */
   int kb;              /* K block (32) */
+  int nt;              /* output-channel tile the weights were packed with (ddg_conv_tile_n) */
   int N, Hout, Wout;   /* output image size */
   int Hp, Wp;          /* padded input space (any source with ntaps > 1): Hout+2 x Wout+2 for 3x3 pad 1 */
   int Cout;
@@ -136,12 +137,15 @@ typedef struct {
                           (wpack + b * ddg_conv_packed_bytes(...)); used for the attention GEMMs (layerspp.py:115-119) */
 } ddg_conv_desc;
 
-int ddg_conv_tile_n(int cout);
-long ddg_conv_packed_bytes(int cout, int total_stages, int kb, int precision);
+/* output-channel tile width the conv kernel will use for a problem with m_rows GEMM rows (pack and launch must agree) */
+int ddg_conv_tile_n(int cout, long m_rows);
+/* tuning switch: use N = 256 output-channel tiles when Cout % 256 == 0 (returns the previous setting) */
+int ddg_conv_set_nt256(int on);
+long ddg_conv_packed_bytes(int cout, int total_stages, int kb, int precision, int nt);
 /* w[co*s_co + ci*s_ci + tap*s_tap] -> packed stages [stage_offset, stage_offset + cin_pad/kb*ntaps) of every n-tile */
 /* batch > 1: `batch` operands, w advances by w_batch_stride floats, out by ddg_conv_packed_bytes(...) bytes per batch */
 int ddg_conv_pack_weights(const float* w, void* out, int cout, int cin_real, int cin_pad, int ntaps, long s_co, long s_ci,
-                          long s_tap, int flip_taps, int kb, int stage_offset, int total_stages, int precision, int batch,
+                          long s_tap, int flip_taps, int kb, int stage_offset, int total_stages, int precision, int nt, int batch,
                           long w_batch_stride, cudaStream_t stream);
 int ddg_conv2d_fwd(const ddg_conv_desc* desc, cudaStream_t stream);
 

@@ -178,7 +178,7 @@ def _conv_case(ops, n, cin, cout, h, k, prec=3, affine=False, act=0, res=False, 
     if res:
         r = seeded((n, cout, h, h), 37)
         ref = (ref + r) / math.sqrt(2)
-    cw = ops.ConvWeights(cout, segs, DEV, precision=prec)
+    cw = ops.ConvWeights(cout, segs, DEV, precision=prec, m_rows=n * (h + 2) * (h + 2) if k == 3 else n * h * h)
     cw.pack_conv_weight(0, w.to(DEV).contiguous())
     scd = shd = None
     if affine:

@@ -5,12 +5,14 @@ import torch
 from ddgan_b200 import ops
 dev = 'cuda'
 names = ['prod_total', 'prod_wait_emptyA', 'prod_wait_acc', 'epilogue', 'loader_total', 'loader_wait_emptyB', 'mma_total', 'mma_wait_A', 'mma_wait_B']
-def run(n, cin, cout, h, k, msub=0, affine=True, prec=3):
+def run(n, cin, cout, h, k, msub=0, affine=True, prec=3, nt256=1):
+    from ddgan_b200._lib import lib
+    lib().ddg_conv_set_nt256(nt256)
     cp = ops.pad_c(cin)
     x = ops.to_pnhwc(torch.randn(n, cin, h, h, device=dev), cpad=cp)
     w = torch.randn(cout, cin, k, k, device=dev) / math.sqrt(cin * k * k)
     taps = ops.TAPS_3X3 if k == 3 else ops.TAPS_1X1
-    cw = ops.ConvWeights(cout, [(cp, len(taps))], dev, precision=prec); cw.pack_conv_weight(0, w)
+    cw = ops.ConvWeights(cout, [(cp, len(taps))], dev, precision=prec, m_rows=n * (h + 2) * (h + 2) if k == 3 else n * h * h); cw.pack_conv_weight(0, w)
     sc = torch.rand(n, cp, device=dev) + 0.5 if affine else None; sh = torch.randn(n, cp, device=dev) if affine else None
     out = ops.alloc_pnhwc(n, h, h, cout, dev)
     st = torch.zeros(n, cout, 2, dtype=torch.float64, device=dev)
@@ -26,13 +28,15 @@ def run(n, cin, cout, h, k, msub=0, affine=True, prec=3):
     ms = e0.elapsed_time(e1) / 10
     fl = 2 * n * h * h * cout * cp * k * k
     pv = prof.cpu().tolist()
-    print(f'conv {cin}->{cout} {k}x{k} @{h}px n={n} msub={msub} prec={prec}: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s')
+    print(f'conv {cin}->{cout} {k}x{k} @{h}px n={n} msub={msub} prec={prec} nt256={nt256}: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s')
     print('   ' + '  '.join(f'{a}={b}' for a, b in zip(names, pv)))
-run(64, 256, 256, 32, 3)
-run(64, 256, 256, 32, 3, msub=1)
-run(64, 256, 256, 32, 3, prec=1)
-run(64, 256, 256, 32, 3, affine=False)
-run(64, 128, 128, 32, 3)
-run(64, 256, 256, 16, 3)
-run(64, 256, 256, 4, 3)
-run(64, 256, 768, 16, 1)
+for nt in (0, 1):
+    for ms in (1, 2):
+        run(64, 256, 256, 32, 3, msub=ms, nt256=nt)
+run(64, 256, 256, 16, 3, msub=1, nt256=0)
+run(64, 256, 256, 16, 3, msub=1, nt256=1)
+run(64, 256, 256, 16, 3, msub=2, nt256=1)
+run(64, 256, 768, 16, 1, nt256=0)
+run(64, 256, 768, 16, 1, nt256=1)
+run(64, 256, 256, 8, 3, nt256=0)
+run(64, 256, 256, 8, 3, nt256=1)

@@ -29,7 +29,7 @@ def run(name, n, cin, cout, h, k, swap=0, msub=0, prec=3, affine=False, act=0, r
     cp = ops.pad_c(cin)
     xd = ops.to_pnhwc(x.to(dev), cpad=cp)
     taps = ops.TAPS_3X3 if k == 3 else ops.TAPS_1X1
-    cw = ops.ConvWeights(cout, [(cp, len(taps))], dev, precision=prec)
+    cw = ops.ConvWeights(cout, [(cp, len(taps))], dev, precision=prec, m_rows=n * (h + 2) * (h + 2) if k == 3 else n * h * h)
     cw.pack_conv_weight(0, w.to(dev).contiguous())
     scd = shd = None
     if affine:
