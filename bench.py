@@ -38,6 +38,8 @@ def parse():
     ap.add_argument('--batch', type=int, default=64, help='images per GPU per step')
     ap.add_argument('--precision', type=int, default=3, help='3 = BF16x3 (fp32 parity mode, headline), 1 = BF16')
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--faithful-wasted-backward', action='store_true',
+                    help='also run the generator backward of the D step whose gradients the reference discards (ddgan.py:489)')
     ap.add_argument('--cpu-sample-batch', type=int, default=8)
     ap.add_argument('--skip-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -205,7 +207,7 @@ def run_b200_train(args, emit=True):
     netG = NCSNpp(cfg).to(dev)
     netD = Discriminator_small(nc=2 * cfg.num_channels, ngf=cfg.ngf, t_emb_dim=cfg.t_emb_dim).to(dev)
     netG.precision = netD.precision = args.precision
-    tr = Trainer(cfg, netG, netD, dev, distributed=world > 1)
+    tr = Trainer(cfg, netG, netD, dev, distributed=world > 1, skip_discarded_g_backward=not args.faithful_wasted_backward)
     real = (torch.rand(B, 3, 32, 32, device=dev) * 2 - 1)
 
     def barrier():
@@ -283,6 +285,8 @@ def run_b200_train(args, emit=True):
                        'T': 4, 'batch_per_gpu': B, 'r1_gamma': 0.02, 'lazy_reg': 15, 'optimizer': 'Adam lr_g 1.6e-4 lr_d 1.25e-4',
                        'parallelism': f'data parallel x{world}: one flat NCCL all-reduce(mean) per network per step',
                        'cuda_graph': use_graph,
+                       'd_step_generator_backward': 'computed (reference-faithful)' if args.faithful_wasted_backward else
+                       'skipped: those G gradients are zeroed by netG.zero_grad() (ddgan.py:489) before any use; parameter updates identical',
                        'l2': 'activations saved for backward (~10 GB per step) exceed the 126 MB L2; no explicit flush'},
             'e2e': {'value': samples / (ms_e2e * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': B * 3 * 32 * 32 * 4, 'd2h_bytes_per_step': 8},
             'gpu_launches': int(n_launch * args.steps),

@@ -88,7 +88,11 @@ class Trainer:
     """args needs: num_timesteps, beta_min, beta_max, use_geometric, nz, lr_g, lr_d, beta1, beta2, r1_gamma, lazy_reg,
     grad_clip_norm, ema_decay (names as in train_ddgan.py)."""
 
-    def __init__(self, args, netG, netD, device, distributed=False):
+    def __init__(self, args, netG, netD, device, distributed=False, skip_discarded_g_backward=True):
+        # ddgan.py:471-477 back-propagates errD_fake through the (un-detached) generator, and ddgan.py:489 zeroes those
+        # generator gradients before anything reads them.  With skip_discarded_g_backward the D step evaluates G under no_grad
+        # (fused inference plan): identical D gradients, identical parameter updates, none of the discarded work.
+        self.skip_discarded_g_backward = skip_discarded_g_backward
         self.args = args
         self.netG, self.netD = netG, netD
         self.dev = device
@@ -134,8 +138,13 @@ class Trainer:
         z = nz.get('z_d')
         if z is None:
             z = torch.randn(B, a.nz, device=self.dev)
-        x_0_predict = netG(x_tp1.detach(), t, z)
-        x_pos_sample = diffusion.sample_posterior(self.pos_coeff, x_0_predict, x_tp1, t, noise=nz.get('n_post_d'))
+        if self.skip_discarded_g_backward:
+            with torch.no_grad():
+                x_0_predict = netG(x_tp1.detach(), t, z)
+                x_pos_sample = diffusion.sample_posterior(self.pos_coeff, x_0_predict, x_tp1.detach(), t, noise=nz.get('n_post_d'))
+        else:
+            x_0_predict = netG(x_tp1.detach(), t, z)
+            x_pos_sample = diffusion.sample_posterior(self.pos_coeff, x_0_predict, x_tp1, t, noise=nz.get('n_post_d'))
         output = netD(x_pos_sample, t, x_tp1.detach()).view(-1)
         errD_fake = F.softplus(output).mean()
         errD_fake.backward()

@@ -145,6 +145,7 @@ def test_trainer_step_and_graph_replay_update_weights():
     netG2, netD2 = copy.deepcopy(netG), copy.deepcopy(netD)
     real = torch.tanh(seeded((4, 3, 32, 32), 300)).to(DEV)
     tr = Trainer(cfg, netG, netD, DEV)
+    assert tr.skip_discarded_g_backward
     w0 = torch.cat([p.detach().flatten() for p in netG.parameters()]).clone()
     for i in range(3):
         errD, errG = tr.step(real, i)
@@ -162,3 +163,29 @@ def test_trainer_step_and_graph_replay_update_weights():
     assert torch.isfinite(wb).all() and torch.isfinite(errD) and torch.isfinite(errG)
     d_graph = float((wb - wa).norm())
     assert 0.2 * d_eager < d_graph < 5 * d_eager, (d_eager, d_graph)
+
+
+def test_skipping_the_discarded_generator_backward_is_exact():
+    """D-step gradients and both parameter updates are identical with and without the generator backward that ddgan.py:489
+    throws away (same injected randomness)."""
+    import copy
+    from ddgan_b200.train import Trainer
+    cfg, netG, netD = _nets()
+    for k, v in dict(lr_g=1.6e-4, lr_d=1.25e-4, beta1=0.5, beta2=0.9, r1_gamma=0.02, lazy_reg=1, grad_clip_norm=1.0,
+                     ema_decay=0.999, use_ema=True).items():
+        setattr(cfg, k, v)
+    netG2, netD2 = copy.deepcopy(netG), copy.deepcopy(netD)
+    real = torch.tanh(seeded((4, 3, 32, 32), 300)).to(DEV)
+    nz = {}
+    for sfx, base in (('_d', 400), ('_g', 500)):
+        nz['t' + sfx] = torch.tensor([0, 1, 2, 3], device=DEV)
+        nz['n_xtp1' + sfx] = seeded((4, 3, 32, 32), base + 1).to(DEV); nz['n_xt' + sfx] = seeded((4, 3, 32, 32), base + 2).to(DEV)
+        nz['z' + sfx] = seeded((4, cfg.nz), base + 3).to(DEV); nz['n_post' + sfx] = seeded((4, 3, 32, 32), base + 4).to(DEV)
+    a = Trainer(cfg, netG, netD, DEV, skip_discarded_g_backward=True)
+    b = Trainer(cfg, netG2, netD2, DEV, skip_discarded_g_backward=False)
+    ea = a.step(real, 0, noise=nz)
+    eb = b.step(real, 0, noise=nz)
+    assert abs(float(ea[0]) - float(eb[0])) < 1e-5 and abs(float(ea[1]) - float(eb[1])) < 1e-5
+    for (n1, p1), (n2, p2) in zip(list(netD.named_parameters()) + list(netG.named_parameters()),
+                                  list(netD2.named_parameters()) + list(netG2.named_parameters())):
+        assert O.rel_l2(p1.detach().cpu(), p2.detach().cpu()) < 2e-5, n1
