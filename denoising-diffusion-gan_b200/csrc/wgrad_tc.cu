@@ -69,9 +69,7 @@ __device__ __forceinline__ void w_tmem_ld32(uint32_t taddr, float* v) {
 
 constexpr int kWProdWarps = 8;
 constexpr int kWThreads = (kWProdWarps + 1) * 32;   // + 1 MMA warp (also owns TMEM alloc)
-constexpr int KT = 128;                              // pixel rows per stage (GEMM K per stage)
 constexpr int MCO = 128;                             // output channels per CTA (GEMM M)
-constexpr int NCI = 32;                              // input channels per CTA (GEMM N per tap)
 
 struct WgradDev {
   const float* x;      // PNHWC source as seen by the conv, pitch xpitch
@@ -83,28 +81,31 @@ struct WgradDev {
   int dy_c;            // channels physically present in dy (load bound)
   int ntaps;
   int tapoff[9];       // row offset of each tap (dr*Wp + ds)
-  int margin;          // max |tapoff|
+  int taps_per_group;  // taps handled by one CTA (their accumulators share the 512 TMEM columns)
+  int ngroups;
   long s_co, s_ci, s_tap;
   int tiles_per_cta;   // pixel tiles per split
   int n_tiles;         // total pixel tiles
-  int xrows, xpitch_b; // X window rows / chunk pitch in bytes
-  int precision;       // 3 or 1 (compile-time NPL mirrors this)
+  int xpitch_b;        // X window chunk pitch in bytes
 };
 
-template <int PREC>
+// NCI: input channels per CTA (GEMM N per tap); KT: pixel rows per stage (GEMM K per stage); NST: smem stages.
+//   <128, 64, 3>: Cin % 128 == 0 -- one tap row (<= 3 taps) per CTA, 128x128x16 MMAs (same operand-read rate as the forward)
+//   < 32, 128, 2>: narrow inputs (3-channel image conv, stddev channel) -- all taps per CTA
+template <int PREC, int NCI, int KT, int NST>
 __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgradDev p) {
   constexpr int NPL = (PREC == 3) ? 2 : 1;
-  constexpr int DY_CH = MCO / 8;                     // 16 chunks
-  constexpr int X_CH = NCI / 8;                      // 4 chunks
-  constexpr int DY_PITCH = (KT + 1) * 16;            // bytes per chunk (odd row count: conflict-free chunk-strided stores)
+  constexpr int DY_CH = MCO / 8;
+  constexpr int X_CH = NCI / 8;
+  constexpr int DY_PITCH = (KT + 1) * 16;            // odd row count: conflict-free chunk-strided stores
   constexpr int DY_PLANE = DY_CH * DY_PITCH;
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   const uint32_t bar_base = w_smem_u32(bars);
   auto full = [&](int s) { return bar_base + 8u * s; };
-  auto empty = [&](int s) { return bar_base + 8u * (2 + s); };
-  const uint32_t accFull = bar_base + 8u * 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 48);
+  auto empty = [&](int s) { return bar_base + 8u * (NST + s); };
+  const uint32_t accFull = bar_base + 8u * (2 * NST);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * NST + 1));
   const int x_plane = X_CH * p.xpitch_b;
   const int stage_bytes = NPL * (DY_PLANE + x_plane);
   uint8_t* sbase = smem + 128;
@@ -112,12 +113,19 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int co0 = blockIdx.x * MCO;
   const int ci0 = blockIdx.y * NCI;
-  const int tile0 = blockIdx.z * p.tiles_per_cta;
+  const int grp = blockIdx.z % p.ngroups;
+  const int split = blockIdx.z / p.ngroups;
+  const int t0 = grp * p.taps_per_group;
+  const int t1 = min(t0 + p.taps_per_group, p.ntaps);
+  int minoff = p.tapoff[t0], maxoff = p.tapoff[t0];
+  for (int t = t0 + 1; t < t1; ++t) { minoff = min(minoff, p.tapoff[t]); maxoff = max(maxoff, p.tapoff[t]); }
+  const int xrows = KT + (maxoff - minoff);
+  const int tile0 = split * p.tiles_per_cta;
   const int tile1 = min(tile0 + p.tiles_per_cta, p.n_tiles);
-  const int my_tiles = tile1 - tile0;
+  const int my_tiles = max(tile1 - tile0, 0);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) { w_mbar_init(full(s), kWProdWarps * 32); w_mbar_init(empty(s), 1); }
+    for (int s = 0; s < NST; ++s) { w_mbar_init(full(s), kWProdWarps * 32); w_mbar_init(empty(s), 1); }
     w_mbar_init(accFull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -134,50 +142,67 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const __grid_con
     // ============================ producers: fp32 rows -> bf16 hi/lo operand tiles ============================
     const int tid = threadIdx.x;
     constexpr int NPT = kWProdWarps * 32;
+    constexpr int UB = 4;                            // independent 32-byte loads in flight per thread
+    auto cvt_store = [&](const float4& a, const float4& b, uint8_t* dst_hi, uint8_t* dst_lo) {
+      uint4 hi, lo;
+      split_bf16x2(a.x, a.y, hi.x, lo.x); split_bf16x2(a.z, a.w, hi.y, lo.y);
+      split_bf16x2(b.x, b.y, hi.z, lo.z); split_bf16x2(b.z, b.w, hi.w, lo.w);
+      *reinterpret_cast<uint4*>(dst_hi) = hi;
+      if (NPL == 2) *reinterpret_cast<uint4*>(dst_lo) = lo;
+    };
     for (int it = 0; it < my_tiles; ++it) {
-      const int st = it & 1;
-      const uint32_t ph = (it >> 1) & 1;
+      const int st = it % NST;
+      const uint32_t ph = (it / NST) & 1;
       const int q0 = (tile0 + it) * KT;
       w_mbar_wait(empty(st), ph ^ 1);
       uint8_t* sdy = sbase + st * stage_bytes;
       uint8_t* sx = sdy + NPL * DY_PLANE;
       // dY tile: KT rows x 16 chunks
-      for (int item = tid; item < KT * DY_CH; item += NPT) {
-        const int c = item % DY_CH, e = item / DY_CH;
-        const int q = q0 + e;
-        float v[8];
-        if (q < p.Mtotal && co0 + c * 8 < p.dy_c) {
-          const float4* src = reinterpret_cast<const float4*>(p.dy + (size_t)q * p.dypitch + co0 + c * 8);
-          const float4 a = __ldg(src), b = __ldg(src + 1);
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        } else {
+      for (int base = tid; base < KT * DY_CH; base += NPT * UB) {
+        float4 a[UB], b[UB];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        for (int u = 0; u < UB; ++u) {
+          const int item = base + u * NPT;
+          const int c = item % DY_CH, e = item / DY_CH;
+          const int q = q0 + e;
+          a[u] = b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (item < KT * DY_CH && q < p.Mtotal && co0 + c * 8 < p.dy_c) {
+            const float4* src = reinterpret_cast<const float4*>(p.dy + (size_t)q * p.dypitch + co0 + c * 8);
+            a[u] = __ldg(src); b[u] = __ldg(src + 1);
+          }
         }
-        uint4 hi, lo;
-        split_bf16x2(v[0], v[1], hi.x, lo.x); split_bf16x2(v[2], v[3], hi.y, lo.y);
-        split_bf16x2(v[4], v[5], hi.z, lo.z); split_bf16x2(v[6], v[7], hi.w, lo.w);
-        *reinterpret_cast<uint4*>(sdy + c * DY_PITCH + e * 16) = hi;
-        if (NPL == 2) *reinterpret_cast<uint4*>(sdy + DY_PLANE + c * DY_PITCH + e * 16) = lo;
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const int item = base + u * NPT;
+          if (item < KT * DY_CH) {
+            const int c = item % DY_CH, e = item / DY_CH;
+            cvt_store(a[u], b[u], sdy + c * DY_PITCH + e * 16, sdy + DY_PLANE + c * DY_PITCH + e * 16);
+          }
+        }
       }
-      // X window: xrows rows x 4 chunks, rows q0 - margin ...
-      for (int item = tid; item < p.xrows * X_CH; item += NPT) {
-        const int c = item % X_CH, e = item / X_CH;
-        const int g = q0 - p.margin + e;
-        float v[8];
-        if (g >= 0 && g < p.Mtotal) {
-          const float4* src = reinterpret_cast<const float4*>(p.x + (size_t)g * p.xpitch + ci0 + c * 8);
-          const float4 a = __ldg(src), b = __ldg(src + 1);
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        } else {
+      // X window: xrows rows x X_CH chunks, rows q0 + minoff ...
+      const int nx = xrows * X_CH;
+      for (int base = tid; base < nx; base += NPT * UB) {
+        float4 a[UB], b[UB];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        for (int u = 0; u < UB; ++u) {
+          const int item = base + u * NPT;
+          const int c = item % X_CH, e = item / X_CH;
+          const int g = q0 + minoff + e;
+          a[u] = b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (item < nx && g >= 0 && g < p.Mtotal) {
+            const float4* src = reinterpret_cast<const float4*>(p.x + (size_t)g * p.xpitch + ci0 + c * 8);
+            a[u] = __ldg(src); b[u] = __ldg(src + 1);
+          }
         }
-        uint4 hi, lo;
-        split_bf16x2(v[0], v[1], hi.x, lo.x); split_bf16x2(v[2], v[3], hi.y, lo.y);
-        split_bf16x2(v[4], v[5], hi.z, lo.z); split_bf16x2(v[6], v[7], hi.w, lo.w);
-        *reinterpret_cast<uint4*>(sx + c * p.xpitch_b + e * 16) = hi;
-        if (NPL == 2) *reinterpret_cast<uint4*>(sx + x_plane + c * p.xpitch_b + e * 16) = lo;
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          const int item = base + u * NPT;
+          if (item < nx) {
+            const int c = item % X_CH, e = item / X_CH;
+            cvt_store(a[u], b[u], sx + c * p.xpitch_b + e * 16, sx + x_plane + c * p.xpitch_b + e * 16);
+          }
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       w_mbar_arrive(full(st));
@@ -187,15 +212,18 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const __grid_con
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int quad = warp & 3, half = warp >> 2;
     const int co = co0 + quad * 32 + lane;
-    for (int t = half; t < p.ntaps; t += 2) {
+    constexpr int NCH = NCI / 32;
+    const int njobs = (t1 - t0) * NCH;
+    for (int job = half; job < njobs; job += 2) {
+      const int tl = job / NCH, ch = job % NCH;
       float v[32];
-      w_tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * NCI), v);
+      w_tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tl * NCI + ch * 32), v);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (co < p.Cout && my_tiles > 0) {
-        float* dst = p.dw + (size_t)co * p.s_co + (size_t)t * p.s_tap;
+        float* dst = p.dw + (size_t)co * p.s_co + (size_t)(t0 + tl) * p.s_tap;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int ci = ci0 + j;
+          const int ci = ci0 + ch * 32 + j;
           if (ci < p.Cin_real) atomicAdd(dst + (size_t)ci * p.s_ci, v[j]);
         }
       }
@@ -204,19 +232,19 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const __grid_con
   } else {
     // ============================ MMA issuer ============================
     if (lane == 0) {
-      // MN-major A and B (bits 15, 16), fp32 accumulate, bf16 inputs, N = 32, M = 128
+      // MN-major A and B (bits 15, 16), fp32 accumulate, bf16 inputs, N = NCI, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NCI >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       for (int it = 0; it < my_tiles; ++it) {
-        const int st = it & 1;
-        w_mbar_wait(full(st), (it >> 1) & 1);
+        const int st = it % NST;
+        w_mbar_wait(full(st), (it / NST) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t dy_hi = w_smem_u32(sbase + st * stage_bytes);
         const uint32_t dy_lo = dy_hi + DY_PLANE;
         const uint32_t x_hi = dy_hi + NPL * DY_PLANE;
         const uint32_t x_lo = x_hi + x_plane;
-        for (int t = 0; t < p.ntaps; ++t) {
-          const uint32_t xoff = (uint32_t)(p.margin + p.tapoff[t]) * 16u;
-          const uint32_t d = tmem_base + (uint32_t)(t * NCI);
+        for (int t = t0; t < t1; ++t) {
+          const uint32_t xoff = (uint32_t)(p.tapoff[t] - minoff) * 16u;
+          const uint32_t d = tmem_base + (uint32_t)((t - t0) * NCI);
 #pragma unroll
           for (int kk = 0; kk < KT / 16; ++kk) {
             const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
@@ -247,13 +275,46 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const __grid_con
   }
 }
 
+template <int PREC, int NCI, int KT, int NST>
+static int launch_wgrad(WgradDev& d, int Cout, int Cin_pad, int group_taps, cudaStream_t stream) {
+  d.taps_per_group = group_taps;
+  d.ngroups = (d.ntaps + group_taps - 1) / group_taps;
+  int span = 0;
+  for (int g = 0; g < d.ngroups; ++g) {
+    int lo = d.tapoff[g * group_taps], hi = lo;
+    for (int t = g * group_taps; t < d.ntaps && t < (g + 1) * group_taps; ++t) { lo = d.tapoff[t] < lo ? d.tapoff[t] : lo; hi = d.tapoff[t] > hi ? d.tapoff[t] : hi; }
+    if (hi - lo > span) span = hi - lo;
+  }
+  int rows = KT + span;
+  if ((rows & 1) == 0) rows += 1;
+  d.xpitch_b = rows * 16;
+  d.n_tiles = (d.Mtotal + KT - 1) / KT;
+  constexpr int NPL = PREC == 3 ? 2 : 1;
+  const size_t stage = (size_t)NPL * ((MCO / 8) * (KT + 1) * 16 + (NCI / 8) * d.xpitch_b);
+  const size_t smem = 128 + NST * stage;
+  if (smem > 227 * 1024) { ddg_set_last_error("conv2d_wgrad: shared memory budget exceeded (image too wide)"); return DDG_ERR_UNSUPPORTED; }
+  const int gx = (Cout + MCO - 1) / MCO, gy = Cin_pad / NCI;
+  const int base = gx * gy * d.ngroups;
+  int splits = (2 * 148 + base - 1) / base;        // ~2 waves of 148 SMs
+  if (splits > d.n_tiles) splits = d.n_tiles;
+  if (splits < 1) splits = 1;
+  d.tiles_per_cta = (d.n_tiles + splits - 1) / splits;
+  splits = (d.n_tiles + d.tiles_per_cta - 1) / d.tiles_per_cta;
+  auto kern = wgrad_tc_kernel<PREC, NCI, KT, NST>;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+  kern<<<dim3(gx, gy, d.ngroups * splits), kWThreads, smem, stream>>>(d);
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}
+
 }  // namespace ddg
 
 using namespace ddg;
 
 extern "C" int ddg_conv2d_wgrad(const ddg_wgrad_desc* c, cudaStream_t stream) {
   if (!c || !c->x || !c->dy || !c->dw || c->ntaps < 1 || c->ntaps > 9) { ddg_set_last_error("conv2d_wgrad: bad args"); return DDG_ERR_ARG; }
-  if (c->Cin_pad % NCI != 0 || c->xpitch % 4 != 0 || c->dypitch % 4 != 0 || c->dy_cpad % 8 != 0) {
+  if (c->Cin_pad % 32 != 0 || c->xpitch % 4 != 0 || c->dypitch % 4 != 0 || c->dy_cpad % 8 != 0) {
     ddg_set_last_error("conv2d_wgrad: channel counts must be padded (Cin to 32, pitches to 4)");
     return DDG_ERR_ARG;
   }
@@ -265,41 +326,15 @@ extern "C" int ddg_conv2d_wgrad(const ddg_wgrad_desc* c, cudaStream_t stream) {
   d.dy_c = c->dy_cpad;
   d.Cin_real = c->Cin_real;
   d.ntaps = c->ntaps;
-  int margin = 0;
-  for (int t = 0; t < c->ntaps; ++t) {
-    d.tapoff[t] = c->tap_dr[t] * c->Wp + c->tap_ds[t];
-    const int a = d.tapoff[t] < 0 ? -d.tapoff[t] : d.tapoff[t];
-    if (a > margin) margin = a;
-  }
-  d.margin = margin;
+  for (int t = 0; t < c->ntaps; ++t) d.tapoff[t] = c->tap_dr[t] * c->Wp + c->tap_ds[t];
   d.s_co = c->s_co; d.s_ci = c->s_ci; d.s_tap = c->s_tap;
-  d.n_tiles = (d.Mtotal + KT - 1) / KT;
-  int rows = KT + 2 * margin;
-  d.xrows = rows;
-  if ((rows & 1) == 0) rows += 1;
-  d.xpitch_b = rows * 16;
   const int prec = c->precision == 1 ? 1 : 3;
-  const int npl = prec == 3 ? 2 : 1;
-  const size_t stage = (size_t)npl * ((MCO / 8) * (KT + 1) * 16 + (NCI / 8) * d.xpitch_b);
-  const size_t smem = 128 + 2 * stage;
-  if (smem > 227 * 1024) { ddg_set_last_error("conv2d_wgrad: shared memory budget exceeded (image too wide)"); return DDG_ERR_UNSUPPORTED; }
-  const int gx = (c->Cout + MCO - 1) / MCO, gy = c->Cin_pad / NCI;
-  // split the pixel space so that the grid is ~2 waves of 148 SMs
-  int splits = (2 * 148 + gx * gy - 1) / (gx * gy);
-  if (splits > d.n_tiles) splits = d.n_tiles;
-  if (splits < 1) splits = 1;
-  d.tiles_per_cta = (d.n_tiles + splits - 1) / splits;
-  splits = (d.n_tiles + d.tiles_per_cta - 1) / d.tiles_per_cta;
-  dim3 grid(gx, gy, splits);
-  if (prec == 3) {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
-    wgrad_tc_kernel<3><<<grid, kWThreads, smem, stream>>>(d);
-  } else {
-    static bool attr1 = false;
-    if (!attr1) { cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr1 = true; }
-    wgrad_tc_kernel<1><<<grid, kWThreads, smem, stream>>>(d);
+  if (c->Cin_pad % 128 == 0) {
+    // one tap row per CTA: 3x3 -> 3 groups of 3, 2x2 -> 2 groups of 2, 1x1 -> 1 group
+    const int gt = c->ntaps == 9 ? 3 : (c->ntaps == 4 ? 2 : (c->ntaps <= 4 ? c->ntaps : 3));
+    return prec == 3 ? launch_wgrad<3, 128, 64, 3>(d, c->Cout, c->Cin_pad, gt, stream)
+                     : launch_wgrad<1, 128, 64, 3>(d, c->Cout, c->Cin_pad, gt, stream);
   }
-  DDG_CHECK_LAUNCH();
-  return DDG_OK;
+  return prec == 3 ? launch_wgrad<3, 32, 128, 2>(d, c->Cout, c->Cin_pad, c->ntaps, stream)
+                   : launch_wgrad<1, 32, 128, 2>(d, c->Cout, c->Cin_pad, c->ntaps, stream);
 }
