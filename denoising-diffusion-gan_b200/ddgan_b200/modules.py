@@ -66,7 +66,9 @@ class _EngineModule(nn.Module):
         self.precision = 3  # 3 = BF16x3 (fp32 parity), 1 = BF16
 
     def _version(self):
-        return sum(p._version for p in self.parameters()) + sum(p.data_ptr() % 1009 for p in self.parameters())
+        # _manual_version is bumped by optimisers that update the parameters through raw pointers (train.FlatAdam)
+        return (sum(p._version for p in self.parameters()) + sum(p.data_ptr() % 1009 for p in self.parameters())
+                + 7919 * getattr(self, '_manual_version', 0))
 
     def _get_engine(self, batch, device, build):
         key = (batch, str(device), self.precision)

@@ -84,11 +84,68 @@ class EMA:
                 p.data.copy_(s)
 
 
+class FlatAdam:
+    """clip_grad_norm_ + Adam (+ EMA) over flat parameter / gradient arenas: 3 launches per step instead of ~40 foreach
+    kernels over hundreds of tensors.  The module's parameters and their .grad become views into the arenas, so the DP
+    all-reduce runs on the gradient arena directly (no flatten / unflatten copies)."""
+
+    def __init__(self, module, lr, betas=(0.5, 0.9), eps=1e-8, weight_decay=0.0, max_norm=0.0, ema_decay=0.0):
+        from . import _lib
+        self._lib = _lib
+        self.module = module
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        dev = self.params[0].device
+        sizes = [((p.numel() + 3) // 4) * 4 for p in self.params]     # keep every view 16-byte aligned
+        n = sum(sizes)
+        self.n = n
+        self.flat_p = torch.zeros(n, device=dev)
+        self.flat_g = torch.zeros(n, device=dev)
+        self.m = torch.zeros(n, device=dev)
+        self.v = torch.zeros(n, device=dev)
+        off = 0
+        self.views = []
+        for p, sz in zip(self.params, sizes):
+            pv = self.flat_p[off:off + p.numel()].view_as(p)
+            pv.copy_(p.data)
+            p.data = pv
+            p.grad = self.flat_g[off:off + p.numel()].view_as(p)
+            self.views.append((off, p.numel()))
+            off += sz
+        self.ema = self.flat_p.clone() if ema_decay > 0 else None
+        self.state = torch.tensor([0.0, lr], device=dev)
+        self.normsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.betas, self.eps, self.wd, self.max_norm, self.ema_decay = betas, eps, weight_decay, max_norm, ema_decay
+
+    def zero_grad(self):
+        self.flat_g.zero_()
+
+    def set_lr(self, lr):
+        self.state[1] = lr
+
+    def step(self):
+        lib, ptr, stream = self._lib.lib(), self._lib.ptr, self._lib.stream
+        nq = None
+        if self.max_norm > 0:
+            self._lib.check(lib.ddg_grad_norm_sq(ptr(self.flat_g), self.n, ptr(self.normsq), stream()), 'grad_norm_sq')
+            nq = self.normsq
+        self._lib.check(lib.ddg_adam_ema_step(ptr(self.flat_p), ptr(self.flat_g), ptr(self.m), ptr(self.v), ptr(self.ema), self.n,
+                                              ptr(self.state), ptr(nq), self.max_norm, self.betas[0], self.betas[1], self.eps,
+                                              self.wd, self.ema_decay, stream()), 'adam_ema_step')
+        # parameters changed behind autograd's back: tell the module so its fused inference engine re-packs its operands
+        self.module._manual_version = getattr(self.module, '_manual_version', 0) + 1
+
+    def ema_state_dict(self, module):
+        out = {}
+        for (name, p), (off, num) in zip([(n_, p_) for n_, p_ in module.named_parameters() if p_.requires_grad], self.views):
+            out[name] = self.ema[off:off + num].view_as(p).clone()
+        return out
+
+
 class Trainer:
     """args needs: num_timesteps, beta_min, beta_max, use_geometric, nz, lr_g, lr_d, beta1, beta2, r1_gamma, lazy_reg,
     grad_clip_norm, ema_decay (names as in train_ddgan.py)."""
 
-    def __init__(self, args, netG, netD, device, distributed=False, skip_discarded_g_backward=True):
+    def __init__(self, args, netG, netD, device, distributed=False, skip_discarded_g_backward=True, fused_optim=True):
         # ddgan.py:471-477 back-propagates errD_fake through the (un-detached) generator, and ddgan.py:489 zeroes those
         # generator gradients before anything reads them.  With skip_discarded_g_backward the D step evaluates G under no_grad
         # (fused inference plan): identical D gradients, identical parameter updates, none of the discarded work.
@@ -101,16 +158,42 @@ class Trainer:
         betas = (getattr(args, 'beta1', 0.5), getattr(args, 'beta2', 0.9))
         # capturable=True keeps the Adam step counters on the device so that the whole step can be a CUDA graph
         cap = torch.device(device).type == 'cuda'
-        self.optD = torch.optim.Adam(netD.parameters(), lr=args.lr_d, betas=betas, capturable=cap, foreach=True)
-        self.optG = torch.optim.Adam(netG.parameters(), lr=args.lr_g, betas=betas, capturable=cap, foreach=True)
+        self.fused_optim = fused_optim and cap
+        wd = getattr(args, 'weight_decay', 0.0) or 0.0
+        if self.fused_optim:
+            # grad-norm -> clip -> Adam -> EMA as one flat-arena pass per network
+            self.optD = FlatAdam(netD, args.lr_d, betas, weight_decay=wd, max_norm=args.grad_clip_norm)
+            self.optG = FlatAdam(netG, args.lr_g, betas, weight_decay=wd, max_norm=args.grad_clip_norm,
+                                 ema_decay=(getattr(args, 'ema_decay', 0.9999) if getattr(args, 'use_ema', True) else 0.0))
+        else:
+            self.optD = torch.optim.Adam(netD.parameters(), lr=args.lr_d, betas=betas, weight_decay=wd, capturable=cap, foreach=True)
+            self.optG = torch.optim.Adam(netG.parameters(), lr=args.lr_g, betas=betas, weight_decay=wd, capturable=cap, foreach=True)
         self._graphs = None
-        self.ema = EMA(netG, getattr(args, 'ema_decay', 0.9999)) if getattr(args, 'use_ema', True) else None
+        self.ema = None
         self.distributed = distributed and dist.is_initialized() and dist.get_world_size() > 1
         if self.distributed:
             broadcast_params(netG.parameters())
             broadcast_params(netD.parameters())
-            self.arG = FlatGradAllReducer(netG.parameters())
-            self.arD = FlatGradAllReducer(netD.parameters())
+            if not self.fused_optim:
+                self.arG = FlatGradAllReducer(netG.parameters())
+                self.arD = FlatGradAllReducer(netD.parameters())
+            elif self.optG.ema is not None:
+                self.optG.ema.copy_(self.optG.flat_p)        # EMA starts from the broadcast weights
+        if not self.fused_optim and getattr(args, 'use_ema', True):
+            self.ema = EMA(netG, getattr(args, 'ema_decay', 0.9999))
+        self.world = dist.get_world_size() if self.distributed else 1
+
+    def _reduce_clip_step(self, opt, net, ar_name):
+        if self.fused_optim:
+            if self.distributed:
+                dist.all_reduce(opt.flat_g)              # the arena IS the bucket: one collective, no copies
+                opt.flat_g.div_(self.world)
+            opt.step()
+        else:
+            if self.distributed:
+                getattr(self, ar_name).allreduce()
+            torch.nn.utils.clip_grad_norm_(net.parameters(), max_norm=self.args.grad_clip_norm)
+            opt.step()
 
     def step(self, real_data, global_step, noise=None):
         """One iteration of ddgan.py:443-518.  `noise` (parity runs) = dict with t_d, n_xtp1_d, n_xt_d, z_d, n_post_d and the
@@ -121,7 +204,10 @@ class Trainer:
         # ---------------- D step ----------------
         for p in netD.parameters():
             p.requires_grad = True
-        netD.zero_grad(set_to_none=False)   # grads stay allocated (outside any CUDA-graph pool) and are zeroed in place
+        if self.fused_optim:
+            self.optD.zero_grad()
+        else:
+            netD.zero_grad(set_to_none=False)   # grads stay allocated (outside any CUDA-graph pool) and are zeroed in place
         t = nz.get('t_d', None)
         if t is None:
             t = torch.randint(0, a.num_timesteps, (B,), device=self.dev)
@@ -149,14 +235,14 @@ class Trainer:
         errD_fake = F.softplus(output).mean()
         errD_fake.backward()
         errD = errD_real.detach() + errD_fake.detach()
-        if self.distributed:
-            self.arD.allreduce()
-        torch.nn.utils.clip_grad_norm_(netD.parameters(), max_norm=a.grad_clip_norm)
-        self.optD.step()
+        self._reduce_clip_step(self.optD, netD, 'arD')
         # ---------------- G step ----------------
         for p in netD.parameters():
             p.requires_grad = False
-        netG.zero_grad(set_to_none=False)
+        if self.fused_optim:
+            self.optG.zero_grad()
+        else:
+            netG.zero_grad(set_to_none=False)
         t = nz.get('t_g', None)
         if t is None:
             t = torch.randint(0, a.num_timesteps, (B,), device=self.dev)
@@ -169,10 +255,7 @@ class Trainer:
         output = netD(x_pos_sample, t, x_tp1.detach()).view(-1)
         errG = F.softplus(-output).mean()
         errG.backward()
-        if self.distributed:
-            self.arG.allreduce()
-        torch.nn.utils.clip_grad_norm_(netG.parameters(), max_norm=a.grad_clip_norm)
-        self.optG.step()
+        self._reduce_clip_step(self.optG, netG, 'arG')
         if self.ema is not None:
             self.ema.step()
         return errD, errG.detach()

@@ -178,6 +178,16 @@ int ddg_stats_fwd(const float* x, double* stats, int N, int H, int W, int C, cud
 /* dx = g1[n][c] + 2 * x * g2[n][c] on the interior, g = [N][C][2] float32 */
 int ddg_stats_bwd(const float* x, const float* g, float* dx, int N, int H, int W, int C, cudaStream_t stream);
 
+/* ---- flat-arena optimiser pass (ddgan.py:484-485, 507-508 clip_grad_norm_ + Adam; ema.py:45-55) --------------------------
+ * out[0] = sum of squares of the gradient arena (float64; zeroed by the call). */
+int ddg_grad_norm_sq(const float* g, long n, double* out, cudaStream_t stream);
+/* One Adam step (torch.optim.Adam semantics, no amsgrad) over flat arenas with the gradient clipped to max_norm using
+ * *normsq (NULL or max_norm <= 0: no clipping) and, when ema != NULL, ema = decay*ema + (1-decay)*p_new.
+ * state: device float[2] = {step count (incremented by the call), learning rate}. */
+int ddg_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, long n, float* state, const double* normsq,
+                      float max_norm, float beta1, float beta2, float eps, float weight_decay, float ema_decay,
+                      cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -189,3 +189,30 @@ def test_skipping_the_discarded_generator_backward_is_exact():
     for (n1, p1), (n2, p2) in zip(list(netD.named_parameters()) + list(netG.named_parameters()),
                                   list(netD2.named_parameters()) + list(netG2.named_parameters())):
         assert O.rel_l2(p1.detach().cpu(), p2.detach().cpu()) < 2e-5, n1
+
+
+def test_flat_adam_matches_torch_clip_adam_ema():
+    """ddg_grad_norm_sq + ddg_adam_ema_step vs clip_grad_norm_ + torch.optim.Adam + the EMA update of ema.py:45-55."""
+    from ddgan_b200.train import FlatAdam
+    torch.manual_seed(3)
+    net_a = torch.nn.Sequential(torch.nn.Linear(37, 53), torch.nn.Linear(53, 11)).to(DEV)
+    import copy
+    net_b = copy.deepcopy(net_a)
+    fa = FlatAdam(net_a, 1.6e-4, (0.5, 0.9), max_norm=1.0, ema_decay=0.999)
+    opt = torch.optim.Adam(net_b.parameters(), lr=1.6e-4, betas=(0.5, 0.9))
+    ema = [p.detach().clone() for p in net_b.parameters()]
+    for it in range(4):
+        x = torch.randn(16, 37, device=DEV) * (10.0 if it % 2 else 0.01)   # exercise both clipped and unclipped steps
+        fa.zero_grad(); opt.zero_grad()
+        (net_a(x) ** 2).sum().backward()
+        (net_b(x) ** 2).sum().backward()
+        fa.step()
+        torch.nn.utils.clip_grad_norm_(net_b.parameters(), 1.0)
+        opt.step()
+        for e, p in zip(ema, net_b.parameters()):
+            e.mul_(0.999).add_(p.detach(), alpha=0.001)
+    for pa, pb in zip(net_a.parameters(), net_b.parameters()):
+        assert O.rel_l2(pa.detach().cpu(), pb.detach().cpu()) < 1e-6
+    sd = fa.ema_state_dict(net_a)
+    for (n, _), e in zip(net_a.named_parameters(), ema):
+        assert O.rel_l2(sd[n].cpu(), e.cpu()) < 1e-6
