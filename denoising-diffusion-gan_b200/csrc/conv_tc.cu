@@ -161,6 +161,10 @@ struct ConvDev {
   int out_mode;                // 0 padded NHWC, 1 NHWC, 2 NCHW
   int out_C;                   // channel pitch of out / res (NHWC modes)
   double* stats;               // [N][Cout][2] or null
+  int tile2d;                  // 1: M tile = (16*MSUB image rows) x 8 columns, window = (16*MSUB+2) x 10 halo (see kernel)
+  int tiles_x, tiles_y;        // 2-D tiles per image
+  int a_sbo;                   // byte distance between 8-row groups of the A operand (128 linear, 160 = 10*16 for 2-D tiles)
+  int sub_stride;              // byte distance between the two 128-row sub-tiles inside the A window
   long long* prof;             // optional: per-role cycle counters of CTA (0,0) (bring-up / tuning aid)
   int batch_rows;              // >0: batched GEMM mode (gather only): blockIdx.z = batch, rows per batch
   long w_batch_stride;         // bytes between the packed B operands of consecutive batches
@@ -229,6 +233,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int m0 = (p.batch_rows > 0 ? blockIdx.z * p.batch_rows : 0) + blockIdx.x * MT;
   const int m_end = p.batch_rows > 0 ? (blockIdx.z + 1) * p.batch_rows : p.Mtotal;
   const int ntile = blockIdx.y;
+  // 2-D tile geometry: 8 columns wide so that every image row of the tile is exactly one 8-row UMMA core-matrix group; the
+  // A operand is then uniformly strided (SBO = 10 entries) inside a (rows+2) x 10 halo window and a tap is still an offset.
+  int t2_n = 0, t2_y0 = 0, t2_x0 = 0;
+  if (p.tile2d) {
+    const int tx = blockIdx.x % p.tiles_x;
+    const int r_ = blockIdx.x / p.tiles_x;
+    t2_n = r_ / p.tiles_y;
+    t2_y0 = (r_ - t2_n * p.tiles_y) * 16 * MSUB;
+    t2_x0 = tx * 8;
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(fullA(s), kProdWarps * 32); mbar_init(emptyA(s), 1); }
@@ -266,7 +280,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       off = -2; nn = 0;
       if (e >= row_hi) return;
       off = -1;
-      if (p.window) {
+      if (p.tile2d) {
+        const int wy = e / 10, wx = e - wy * 10;
+        const int y = t2_y0 - 1 + wy, x = t2_x0 - 1 + wx;     // image coordinates; the PNHWC buffer holds the zero border
+        nn = t2_n;
+        const bool inside = (y >= 0) && (y < p.Hout) && (x >= 0) && (x < p.Wout);
+        if (y <= p.Hout && (inside || S.scale == nullptr))
+          off = ((t2_n * (p.Hout + 2) + y + 1) * (p.Wout + 2) + (x + 1)) * S.pitch;
+      } else if (p.window) {
         const int g = m0 - p.margin + e;             // row in padded linear space
         if (g >= 0 && g < p.Mtotal) {
           const int img = p.Hp * p.Wp;
@@ -297,7 +318,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     };
     auto src_rows = [&](const SrcDev& S, int& row_lo, int& row_hi) {
       row_lo = 0; row_hi = p.win_rows;
-      if (p.window && S.ntaps == 1) { row_lo = S.tapoff[0]; row_hi = S.tapoff[0] + MT; }
+      if (p.window && !p.tile2d && S.ntaps == 1) { row_lo = S.tapoff[0]; row_hi = S.tapoff[0] + MT; }
     };
     auto transform_store = [&](const SrcDev& S, float* v, bool live, int n, int ch0, int& cur_n, float* sc, float* sh,
                                uint8_t* dst_hi, uint8_t* dst_lo, int e) {
@@ -436,7 +457,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     for (int sub = 0; sub < MSUB; ++sub) {
       const int m = m0 + sub * 128 + quad * 32 + lane;
       bool valid; int n, h, w;
-      decode_out_row(p, m, m_end, valid, n, h, w);
+      if (p.tile2d) {
+        const int ml = sub * 128 + quad * 32 + lane;
+        n = t2_n; h = t2_y0 + (ml >> 3); w = t2_x0 + (ml & 7);
+        valid = (h < p.Hout) && (w < p.Wout);
+      } else {
+        decode_out_row(p, m, m_end, valid, n, h, w);
+      }
       size_t obase = 0;
       if (p.out_mode == 0) obase = ((size_t)(n * (p.Hout + 2) + h + 1) * (p.Wout + 2) + (w + 1)) * p.out_C;
       else if (p.out_mode == 1) obase = ((size_t)(n * p.Hout + h) * p.Wout + w) * p.out_C;
@@ -590,7 +617,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       // K-major SWIZZLE_NONE: LBO = byte distance between the two 8-element K halves of one MMA (chunk pitch),
       // SBO = byte distance between 8-row groups (rows are 16 B apart, so 128 B).  Verified on B200.
-      const uint32_t a_lbo = (uint32_t)p.win_pitch, a_sbo = 128u;
+      const uint32_t a_lbo = (uint32_t)p.win_pitch, a_sbo = (uint32_t)p.a_sbo;
       const uint32_t b_lbo = (uint32_t)(NT * 16), b_sbo = 128u;
       int kb_idx = 0, bi = 0;
       uint32_t acc = 0;
@@ -617,7 +644,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               uint32_t acc_s = acc;
 #pragma unroll
               for (int kk = 0; kk < KB / 16; ++kk) {
-                const uint32_t aoff = toff + (uint32_t)(sub * 128 * 16) + (uint32_t)(kk * 2) * (uint32_t)p.win_pitch;
+                const uint32_t aoff = toff + (uint32_t)sub * (uint32_t)p.sub_stride + (uint32_t)(kk * 2) * (uint32_t)p.win_pitch;
                 const uint32_t boff = (uint32_t)(kk * 2) * (uint32_t)(NT * 16);
                 const uint64_t dah = make_smem_desc(a_hi + aoff, a_lbo, a_sbo);
                 const uint64_t dbh = make_smem_desc(b_hi + boff, b_lbo, b_sbo);
@@ -732,6 +759,7 @@ static int launch_conv(const ConvDev& d, int n_tiles, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((d.Mtotal + Cfg::MT - 1) / Cfg::MT, n_tiles);
+  if (d.tile2d) grid = dim3(d.N * d.tiles_x * d.tiles_y, n_tiles);
   if (d.batch_rows > 0) grid = dim3((d.batch_rows + Cfg::MT - 1) / Cfg::MT, n_tiles, d.Mtotal / d.batch_rows);
   kern<<<grid, kThreads, smem, stream>>>(d);
   DDG_CHECK_LAUNCH();
@@ -835,17 +863,37 @@ extern "C" int ddg_conv2d_fwd(const ddg_conv_desc* c, cudaStream_t stream) {
   if (!valid_nt(nt)) { ddg_set_last_error("conv2d_fwd: desc.nt must be the tile width the weights were packed with (16/64/128/256)"); return DDG_ERR_ARG; }
   const int n_tiles = (c->Cout + nt - 1) / nt;
   if (d.out_mode != 2 && (c->Cout % (nt >= 64 ? 32 : 16) != 0)) { ddg_set_last_error("conv2d_fwd: Cout must be a multiple of the epilogue chunk for NHWC output"); return DDG_ERR_UNSUPPORTED; }
+  // 2-D tiles (16*msub rows x 8 columns) whenever the geometry allows: no padded-space waste, window independent of W
+  bool tile2d = window && !c->force_linear && d.Hp == d.Hout + 2 && d.Wp == d.Wout + 2 && d.Wout % 8 == 0 && d.Hout % 16 == 0 &&
+                c->batch_rows == 0;
+  for (int s = 0; s < c->nsrc && tile2d; ++s)
+    for (int t = 0; t < c->src[s].ntaps; ++t)
+      if (c->src[s].tap_dr[t] < -1 || c->src[s].tap_dr[t] > 1 || c->src[s].tap_ds[t] < -1 || c->src[s].tap_ds[t] > 1) tile2d = false;
   // M sub-tiles: two accumulators per CTA when the grid still fills the machine
   int msub = c->msub;
   if (msub == 0) {
-    const long tiles2 = ((long)d.Mtotal + 255) / 256 * n_tiles;
+    const long tiles2 = tile2d ? (long)d.N * (d.Hout / 32) * (d.Wout / 8) * n_tiles : ((long)d.Mtotal + 255) / 256 * n_tiles;
     msub = (tiles2 >= 222) ? 2 : 1;   // >= 1.5 waves of 256-row tiles
     if (d.batch_rows > 0 && d.batch_rows % 256 != 0) msub = 1;
   }
+  if (tile2d && d.Hout % (16 * msub) != 0) msub = 1;
   const int MT = 128 * msub;
-  int rows = window ? MT + 2 * d.margin : MT;
+  d.tile2d = tile2d ? 1 : 0;
+  d.a_sbo = 128;
+  d.sub_stride = 128 * 16;
+  if (tile2d) {
+    d.tiles_x = d.Wout / 8;
+    d.tiles_y = d.Hout / (16 * msub);
+    d.a_sbo = 10 * 16;
+    d.sub_stride = 16 * 10 * 16;
+    d.win_rows = (16 * msub + 2) * 10;
+    for (int s = 0; s < c->nsrc; ++s)
+      for (int t = 0; t < c->src[s].ntaps; ++t) d.src[s].tapoff[t] = (c->src[s].tap_dr[t] + 1) * 10 + (c->src[s].tap_ds[t] + 1);
+  } else {
+    d.win_rows = window ? MT + 2 * d.margin : MT;
+  }
+  int rows = d.win_rows;
   if ((rows & 1) == 0) rows += 1;                   // odd pitch (in 16-byte units): conflict-free chunk-strided stores
-  d.win_rows = window ? MT + 2 * d.margin : MT;
   d.win_pitch = rows * 16;
   const int prec = c->precision == 1 ? 1 : 3;
 

@@ -332,7 +332,7 @@ def _addr(v):
 
 
 def build_conv_desc(weights: ConvWeights, srcs, n, hout, wout, out, out_mode=OUT_PNHWC, hp=None, wp=None, bias=None, addvec=None,
-                    addvec_stride=0, res=None, out_scale=1.0, out_act=ACT_NONE, out_c=0, stats=None, msub=0, batch_rows=0, prof=None) -> ConvDesc:
+                    addvec_stride=0, res=None, out_scale=1.0, out_act=ACT_NONE, out_c=0, stats=None, msub=0, batch_rows=0, prof=None, force_linear=0) -> ConvDesc:
     d = ConvDesc()
     d.nsrc = len(srcs)
     for i, s in enumerate(srcs):
@@ -358,6 +358,7 @@ def build_conv_desc(weights: ConvWeights, srcs, n, hout, wout, out, out_mode=OUT
     d.msub = msub
     d.batch_rows = batch_rows
     d.debug_prof = _addr(prof)
+    d.force_linear = force_linear
     return d
 
 

@@ -132,6 +132,7 @@ typedef struct {
   double* stats;       /* [N][Cout][2] running sum / sum of squares of the stored values, or NULL */
   int precision;       /* 3 = BF16x3 split (fp32 parity), 1 = plain BF16 */
   int msub;            /* 0 auto, 1 or 2 accumulators of 128 rows per CTA */
+  int force_linear;    /* 1: keep the 1-D padded-linear M tiling even where the 2-D (16 x 8) tiling applies (testing) */
   void* debug_prof;    /* optional int64[16] device buffer: per-role cycle counters of one CTA (tuning aid), or NULL */
   int batch_rows;      /* >0: batched GEMM (1x1 only): rows [b*batch_rows, (b+1)*batch_rows) use packed operand b
                           (wpack + b * ddg_conv_packed_bytes(...)); used for the attention GEMMs (layerspp.py:115-119) */

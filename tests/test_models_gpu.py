@@ -89,7 +89,6 @@ def test_discriminator_small_vs_oracle(golden):
     assert O.rel_l2(y.cpu(), ref) < TOL
 
 
-@pytest.mark.xfail(reason='256-px maps need the segmented-window tiling (smem budget); scheduled with the HQ256 configs', strict=False)
 def test_discriminator_large_vs_golden(golden):
     from ddgan_b200.engine import DiscriminatorEngine
     sd = O.randomize_params(O.discriminator_param_shapes(6, 8, 32, large=True), seed=10)

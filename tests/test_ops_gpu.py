@@ -147,7 +147,7 @@ def test_layout_roundtrip_and_fir(ops):
     assert O.rel_l2(s2d[:, 1:6, 1:6, :].cpu(), cells) < 1e-5
 
 
-def _conv_case(ops, n, cin, cout, h, k, prec=3, affine=False, act=0, res=False, nchw=False, msub=0, temb=False, skip1x1=0):
+def _conv_case(ops, n, cin, cout, h, k, prec=3, affine=False, act=0, res=False, nchw=False, msub=0, temb=False, skip1x1=0, force_linear=0):
     x = seeded((n, cin, h, h), 30)
     w = seeded((cout, cin, k, k), 31) / math.sqrt(cin * k * k)
     b = seeded((cout,), 32, 0.1)
@@ -197,7 +197,7 @@ def _conv_case(ops, n, cin, cout, h, k, prec=3, affine=False, act=0, res=False, 
         rd = ops.to_pnhwc(r.to(DEV), cpad=cout) if res else None
     ops.conv2d_fused(cw, srcs, n, h, h, out, out_mode=mode, bias=b.to(DEV), res=rd,
                      out_scale=(1 / math.sqrt(2) if res else 1.0), stats=st, msub=msub,
-                     addvec=(tv.to(DEV) if temb else None), addvec_stride=cout)
+                     addvec=(tv.to(DEV) if temb else None), addvec_stride=cout, force_linear=force_linear)
     y = out if nchw else ops.from_pnhwc(out, cout)
     err = O.rel_l2(y.cpu(), ref)
     s1 = ref.double().sum(dim=(2, 3)); s2 = (ref.double() ** 2).sum(dim=(2, 3))
@@ -227,6 +227,17 @@ def test_conv_tc_fused_variants(ops):
     # fused 1x1 skip conv as a second K segment + residual rescale (ResnetBlockBigGANpp_Adagn, layerspp.py:305-310)
     err, e1, e2 = _conv_case(ops, 4, 256, 128, 16, 3, affine=True, act=1, skip1x1=384)
     assert err < 2e-5 and e1 < 5e-5 and e2 < 5e-5, (err, e1, e2)
+
+
+def test_conv_tc_linear_and_2d_tilings_agree(ops):
+    # 16/32-px maps use the 2-D (16 x 8) tiling by default; the 1-D padded-linear tiling must give the same answer
+    for (n, cin, cout, h) in [(4, 64, 128, 16), (2, 128, 256, 32), (2, 32, 64, 64)]:
+        e2d, _, _ = _conv_case(ops, n, cin, cout, h, 3, affine=True, act=1, res=True)
+        e1d, _, _ = _conv_case(ops, n, cin, cout, h, 3, affine=True, act=1, res=True, force_linear=1)
+        assert e2d < 2e-5 and e1d < 2e-5, (e2d, e1d)
+    for msub in (1, 2):
+        err, e1, e2 = _conv_case(ops, 3, 64, 64, 32, 3, msub=msub, skip1x1=64)
+        assert err < 2e-5 and e1 < 5e-5 and e2 < 5e-5
 
 
 def test_conv_tc_bf16_mode(ops):
