@@ -141,3 +141,10 @@ def test_sampler_vs_oracle(golden):
         smp.z_noise[k].copy_(d2[2 * k]); smp.p_noise[k].copy_(d2[2 * k + 1])
     y = smp.sample(x_init.to(DEV), fresh_noise=False)
     assert O.rel_l2(y.cpu(), golden['sample_tiny']) < TOL
+
+
+def test_generator_hq256_vs_oracle():
+    """BASELINE configs[2]/[3]: CelebA-HQ / LSUN 256-px NCSN++ (ch 64, ch_mult 1-1-2-2-4-4); B = 1 keeps the CPU oracle fast."""
+    cfg = O.celebahq256_config()
+    err, eng = _gen_case(cfg, 1, 31)
+    assert err < TOL, err
