@@ -24,6 +24,7 @@ __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* 
 
 // y[n][j] = act_out(sum_k act_in(x[n][k]) W[j][k] + b[j]); one warp per output column, rows tiled by 32 in smem.
 constexpr int kLinRows = 32;
+constexpr int kLinKC = 1024;   // K chunk of the long-K variant
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                      const float* __restrict__ b, float* __restrict__ y, int N, int K, int J,
                                                      int ldx, int ldy, int act_in, int act_out, int pixel_norm, int cpw) {
@@ -54,6 +55,46 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x
       for (int k = lane; k < K; k += 32) acc = fmaf(sx[r * K + k], __ldg(wr + k), acc);
       acc = warp_sum(acc);
       if (lane == 0) y[(size_t)(n0 + r) * ldy + j] = apply_act(acc + bj, act_out);
+    }
+  }
+}
+
+// long-K variant (K > ~1500: the input-gradient GEMM of the batched style projection, K = 2 * sum(C) ~ 31 K):
+// K is streamed through shared memory in chunks; each lane keeps a partial sum per row in registers.
+__global__ void __launch_bounds__(256) linear_longk_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                           const float* __restrict__ b, float* __restrict__ y, int N, int K, int J,
+                                                           int ldx, int ldy, int act_in, int act_out) {
+  extern __shared__ float sx[];  // [kLinRows][kLinKC]
+  const int n0 = blockIdx.y * kLinRows;
+  const int rows = min(kLinRows, N - n0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + warp;
+  float acc[kLinRows];
+#pragma unroll
+  for (int r = 0; r < kLinRows; ++r) acc[r] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += kLinKC) {
+    const int kc = min(kLinKC, K - k0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * kc; i += blockDim.x) {
+      const int r = i / kc, k = i - r * kc;
+      sx[r * kLinKC + k] = apply_act(x[(size_t)(n0 + r) * ldx + k0 + k], act_in);
+    }
+    __syncthreads();
+    if (j < J) {
+      const float* wr = W + (size_t)j * K + k0;
+      for (int k = lane; k < kc; k += 32) {
+        const float wv = __ldg(wr + k);
+#pragma unroll
+        for (int r = 0; r < kLinRows; ++r) acc[r] = fmaf(sx[r * kLinKC + k], wv, acc[r]);
+      }
+    }
+  }
+  if (j < J) {
+    const float bj = b ? b[j] : 0.f;
+#pragma unroll
+    for (int r = 0; r < kLinRows; ++r) {
+      const float v = warp_sum(acc[r]);
+      if (lane == 0 && r < rows) y[(size_t)(n0 + r) * ldy + j] = apply_act(v + bj, act_out);
     }
   }
 }
@@ -296,7 +337,15 @@ extern "C" int ddg_linear(const float* x, const float* W, const float* b, float*
                           int act_in, int act_out, int pixel_norm, cudaStream_t stream) {
   if (!x || !W || !y || N <= 0 || K <= 0 || J <= 0) { ddg_set_last_error("linear: bad args"); return DDG_ERR_ARG; }
   const size_t smem = (size_t)kLinRows * K * sizeof(float);
-  if (smem > 200 * 1024) { ddg_set_last_error("linear: K too large"); return DDG_ERR_UNSUPPORTED; }
+  if (smem > 200 * 1024) {
+    if (pixel_norm) { ddg_set_last_error("linear: pixel_norm needs K <= 1600"); return DDG_ERR_UNSUPPORTED; }
+    static bool attr2 = false;
+    if (!attr2) { cudaFuncSetAttribute(linear_longk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr2 = true; }
+    dim3 grid2((J + 7) / 8, (N + kLinRows - 1) / kLinRows);
+    linear_longk_kernel<<<grid2, 256, (size_t)kLinRows * kLinKC * sizeof(float), stream>>>(x, W, b, y, N, K, J, ldx, ldy, act_in, act_out);
+    DDG_CHECK_LAUNCH();
+    return DDG_OK;
+  }
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
   const int cpw = J <= 2048 ? 1 : 4;

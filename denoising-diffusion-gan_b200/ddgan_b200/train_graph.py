@@ -349,10 +349,25 @@ def generator_forward(mod, x, time_cond, z):
     temb = LinearFn.apply(F.silu(temb), P['all_modules.1.weight'], P['all_modules.1.bias'])
     temb_act = F.silu(temb)
 
+    # all AdaGN style projections (layerspp.py:57) and all Dense_0 projections (layerspp.py:298-299) as two batched GEMMs
+    style_names = [k[:-7] for k in P if k.endswith('.style.weight')]
+    dense_names = [k[:-7] for k in P if k.endswith('Dense_0.weight')]
+    style_all = LinearFn.apply(zemb, torch.cat([P[k + '.weight'] for k in style_names], 0),
+                               torch.cat([P[k + '.bias'] for k in style_names], 0))
+    dense_all = LinearFn.apply(temb_act, torch.cat([P[k + '.weight'] for k in dense_names], 0),
+                               torch.cat([P[k + '.bias'] for k in dense_names], 0))
+    style_off, dense_off = {}, {}
+    o = 0
+    for k in style_names:
+        style_off[k] = o; o += P[k + '.weight'].shape[0]
+    o = 0
+    for k in dense_names:
+        dense_off[k] = o; o += P[k + '.weight'].shape[0]
+
     def adagn(t, h, w, prefix, act=ops.ACT_SILU):
         c = t.shape[-1]
-        style = LinearFn.apply(zemb, P[prefix + '.style.weight'], P[prefix + '.style.bias'])
-        return group_norm_act(t, h, w, _groups(c), style[:, :c], style[:, c:], act)
+        o_ = style_off[prefix + '.style']
+        return group_norm_act(t, h, w, _groups(c), style_all[:, o_:o_ + c], style_all[:, o_ + c:o_ + 2 * c], act)
 
     def resblock(m, t, h, w):
         pn = f"all_modules.{m['idx']}."
@@ -363,7 +378,7 @@ def generator_forward(mod, x, time_cond, z):
             hh, xs, h, w = fir_up(hh), fir_up(xs), 2 * h, 2 * w
         elif m['down']:
             hh, xs, h, w = fir_down(hh), fir_down(xs), h // 2, w // 2
-        dense = LinearFn.apply(temb_act, P[pn + 'Dense_0.weight'], P[pn + 'Dense_0.bias'])
+        dense = dense_all[:, dense_off[pn + 'Dense_0']:dense_off[pn + 'Dense_0'] + cout]
         hh = conv3x3(hh, P[pn + 'Conv_0.weight'], P[pn + 'Conv_0.bias'], N, h, w, addvec=dense, prec=prec)
         hh = adagn(hh, h, w, pn + 'GroupNorm_1')
         if drop > 0:
