@@ -87,6 +87,32 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// Same MMA with the two 64-bit shared-memory descriptors passed as (lo, hi) 32-bit halves: the hi half (SBO, version) and the
+// LBO field of the lo half are loop invariants, so advancing an operand is one 32-bit add on the issuing thread.
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, P;\n"
+      "}\n" : "=r"(pred));
+  return pred;
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
@@ -613,67 +639,77 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     __syncwarp();
   } else {
     // =================================== MMA issuer ===================================
-    if (lane == 0) {
+    // The whole warp stays converged (all lanes wait on the barriers); one elected lane issues.  The first version ran this loop
+    // inside `if (lane == 0)`, rebuilt four 64-bit descriptors per MMA triple and paid compiler-inserted elect / R2UR sequences
+    // per instruction: ~110 cycles per tcgen05.mma *issue*, independent of N -- i.e. issue-bound below N = 256.
+    {
+      const uint32_t leader = elect_one();
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       // K-major SWIZZLE_NONE: LBO = byte distance between the two 8-element K halves of one MMA (chunk pitch),
-      // SBO = byte distance between 8-row groups (rows are 16 B apart, so 128 B).  Verified on B200.
-      const uint32_t a_lbo = (uint32_t)p.win_pitch, a_sbo = (uint32_t)p.a_sbo;
-      const uint32_t b_lbo = (uint32_t)(NT * 16), b_sbo = 128u;
-      int kb_idx = 0, bi = 0;
+      // SBO = byte distance between 8-row groups (128 B linear tiles, 160 B for 2-D tiles).  Verified on B200.
+      const uint32_t a_hi32 = ((uint32_t)p.a_sbo >> 4) | (1u << 14);                 // descriptor bits 32..63
+      const uint32_t b_hi32 = (128u >> 4) | (1u << 14);
+      const uint32_t a_lbo_f = (((uint32_t)p.win_pitch >> 4) & 0x3FFF) << 16;         // LBO field of the low word
+      const uint32_t b_lbo_f = (((uint32_t)(NT * 16) >> 4) & 0x3FFF) << 16;
+      const uint32_t a_kk16 = (2u * (uint32_t)p.win_pitch) >> 4;                      // +16 channels, in 16-byte units
+      constexpr uint32_t b_kk16 = (2u * NT * 16u) >> 4;
+      const uint32_t a_sub16 = (uint32_t)p.sub_stride >> 4;
+      int bi = 0;
       uint32_t acc = 0;
       long long w_fullA = 0, w_fullB = 0;
       const long long t_m0 = clock64();
-      for (int s = 0; s < p.nsrc; ++s) {
-        const SrcDev& S = p.src[s];
-        for (int kb = 0; kb < S.C / KB; ++kb, ++kb_idx) {
-          const int stA = kb_idx & 1;
-          { const long long tw = clock64(); mbar_wait(fullA(stA), (kb_idx >> 1) & 1); w_fullA += clock64() - tw; }
+      int s_m = 0, kb_m = 0;
+      for (int kb_idx = 0; kb_idx < nkb_total; ++kb_idx) {
+        const SrcDev& S = p.src[s_m];
+        const int stA = kb_idx & 1;
+        { const long long tw = clock64(); mbar_wait(fullA(stA), (kb_idx >> 1) & 1); w_fullA += clock64() - tw; }
+        const uint32_t a_hi_lo = a_lbo_f | (smem_u32(sA + stA * a_stage) >> 4);
+        const uint32_t a_lo_lo = a_lbo_f | (smem_u32(sA + stA * a_stage + a_plane) >> 4);
+        for (int t = 0; t < S.ntaps; ++t, ++bi) {
+          const int stB = bi % NSB;
+          { const long long tw = clock64(); mbar_wait(fullB(stB), (bi / NSB) & 1); w_fullB += clock64() - tw; }
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(sA + stA * a_stage);
-          const uint32_t a_lo = a_hi + a_plane;
-          for (int t = 0; t < S.ntaps; ++t, ++bi) {
-            const int stB = bi % NSB;
-            { const long long tw = clock64(); mbar_wait(fullB(stB), (bi / NSB) & 1); w_fullB += clock64() - tw; }
-            tc_fence_after();
-            const uint32_t b_hi = smem_u32(sB + stB * Cfg::B_STAGE);
-            const uint32_t b_lo = b_hi + Cfg::B_PLANE;
-            const uint32_t toff = (uint32_t)(p.window ? S.tapoff[t] : 0) * 16u;
+          if (leader) {
+            const uint32_t b_hi_lo = b_lbo_f | (smem_u32(sB + stB * Cfg::B_STAGE) >> 4);
+            const uint32_t b_lo_lo = b_lbo_f | (smem_u32(sB + stB * Cfg::B_STAGE + Cfg::B_PLANE) >> 4);
+            const uint32_t toff16 = (uint32_t)(p.window ? S.tapoff[t] : 0);          // rows are 16 B: row offset == 16-byte units
 #pragma unroll
             for (int sub = 0; sub < MSUB; ++sub) {
               const uint32_t d = tmem_base + (uint32_t)(sub * NT);
               uint32_t acc_s = acc;
 #pragma unroll
               for (int kk = 0; kk < KB / 16; ++kk) {
-                const uint32_t aoff = toff + (uint32_t)sub * (uint32_t)p.sub_stride + (uint32_t)(kk * 2) * (uint32_t)p.win_pitch;
-                const uint32_t boff = (uint32_t)(kk * 2) * (uint32_t)(NT * 16);
-                const uint64_t dah = make_smem_desc(a_hi + aoff, a_lbo, a_sbo);
-                const uint64_t dbh = make_smem_desc(b_hi + boff, b_lbo, b_sbo);
+                const uint32_t ao = toff16 + (uint32_t)sub * a_sub16 + (uint32_t)kk * a_kk16;
+                const uint32_t bo = (uint32_t)kk * b_kk16;
                 if (PREC == 3) {
-                  const uint64_t dal = make_smem_desc(a_lo + aoff, a_lbo, a_sbo);
-                  const uint64_t dbl = make_smem_desc(b_lo + boff, b_lbo, b_sbo);
-                  umma_bf16(d, dal, dbh, idesc, acc_s);
-                  umma_bf16(d, dah, dbl, idesc, 1u);
-                  umma_bf16(d, dah, dbh, idesc, 1u);
+                  umma_bf16_lohi(d, a_lo_lo + ao, a_hi32, b_hi_lo + bo, b_hi32, idesc, acc_s);
+                  umma_bf16_lohi(d, a_hi_lo + ao, a_hi32, b_lo_lo + bo, b_hi32, idesc, 1u);
+                  umma_bf16_lohi(d, a_hi_lo + ao, a_hi32, b_hi_lo + bo, b_hi32, idesc, 1u);
                 } else {
-                  umma_bf16(d, dah, dbh, idesc, acc_s);
+                  umma_bf16_lohi(d, a_hi_lo + ao, a_hi32, b_hi_lo + bo, b_hi32, idesc, acc_s);
                 }
                 acc_s = 1u;
               }
             }
-            acc = 1u;
             umma_commit(emptyB(stB));
           }
-          umma_commit(emptyA(stA));
+          acc = 1u;
+          __syncwarp();
+        }
+        if (leader) umma_commit(emptyA(stA));
+        __syncwarp();
+        if (++kb_m >= S.C / KB) { kb_m = 0; ++s_m; }
+      }
+      if (leader) {
+        umma_commit(accFull);
+        if (p.prof != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) {
+          p.prof[6] = clock64() - t_m0;  // MMA issue loop total
+          p.prof[7] = w_fullA;           // ... waiting for A
+          p.prof[8] = w_fullB;           // ... waiting for B
         }
       }
-      umma_commit(accFull);
-      if (p.prof != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) {
-        p.prof[6] = clock64() - t_m0;  // MMA issue loop total
-        p.prof[7] = w_fullA;           // ... waiting for A
-        p.prof[8] = w_fullB;           // ... waiting for B
-      }
+      __syncwarp();
     }
-    __syncwarp();
   }
 
   __syncthreads();
@@ -736,6 +772,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
 // ---------------------------------------------------------------------------------------------------------
 struct Variant { int msub, nt, kb; };
 
+static int g_small_nt64 = 1;
 static int g_nt256 = 1;  // N = 256 tiles for Cout % 256 == 0 (96 B/clk of operand reads per MMA instead of 128 B/clk at N = 128)
 
 // Output-channel tile.  N = 256 only when the grid still covers the machine (one wave of 128-row tiles at least).
@@ -743,6 +780,8 @@ static int pick_nt(int cout, long m_rows) {
   if (cout <= 16) return 16;
   if (cout <= 64) return 64;
   if (g_nt256 && cout % 256 == 0 && ((m_rows + 127) / 128) * (cout / 256) >= 148) return 256;
+  // tiny spatial levels (4x4, 8x8): narrow tiles multiply the CTA count and shorten each CTA's serial MMA chain
+  if (g_small_nt64 && cout % 64 == 0 && ((m_rows + 127) / 128) * ((cout + 127) / 128) < 100) return 64;
   return 128;
 }
 static bool valid_nt(int nt) { return nt == 16 || nt == 64 || nt == 128 || nt == 256; }
@@ -771,7 +810,7 @@ static int launch_conv(const ConvDev& d, int n_tiles, cudaStream_t stream) {
 using namespace ddg;
 
 extern "C" int ddg_conv_tile_n(int cout, long m_rows) { return pick_nt(cout, m_rows); }
-extern "C" int ddg_conv_set_nt256(int on) { const int old = g_nt256; g_nt256 = on ? 1 : 0; return old; }
+extern "C" int ddg_conv_set_nt256(int on) { const int old = g_nt256; g_nt256 = on & 1; g_small_nt64 = (on >> 1) & 1 ? 0 : 1; return old; }
 
 extern "C" long ddg_conv_packed_bytes(int cout, int total_stages, int kb, int precision, int nt) {
   if (!valid_nt(nt)) return -1;

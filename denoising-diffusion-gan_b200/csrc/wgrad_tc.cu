@@ -231,42 +231,55 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const __grid_con
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   } else {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
+    // converged warp, one elected lane issues; descriptors advance with one 32-bit add (see conv_tc.cu)
+    {
+      uint32_t leader;
+      asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.b32 %0, 1, 0, P;\n}\n" : "=r"(leader));
       // MN-major A and B (bits 15, 16), fp32 accumulate, bf16 inputs, N = NCI, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(NCI >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      // MN-major SWIZZLE_NONE: LBO = 128 B (next 8 K rows), SBO = chunk pitch (next 8 M/N channels)
+      const uint32_t lbo_f = ((128u >> 4) & 0x3FFF) << 16;
+      const uint32_t a_hi32 = (((uint32_t)DY_PITCH >> 4) & 0x3FFF) | (1u << 14);
+      const uint32_t b_hi32 = (((uint32_t)p.xpitch_b >> 4) & 0x3FFF) | (1u << 14);
       for (int it = 0; it < my_tiles; ++it) {
         const int st = it % NST;
         w_mbar_wait(full(st), (it / NST) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t dy_hi = w_smem_u32(sbase + st * stage_bytes);
-        const uint32_t dy_lo = dy_hi + DY_PLANE;
-        const uint32_t x_hi = dy_hi + NPL * DY_PLANE;
-        const uint32_t x_lo = x_hi + x_plane;
-        for (int t = t0; t < t1; ++t) {
-          const uint32_t xoff = (uint32_t)(p.tapoff[t] - minoff) * 16u;
-          const uint32_t d = tmem_base + (uint32_t)((t - t0) * NCI);
+        if (leader) {
+          const uint32_t dy_hi = lbo_f | (w_smem_u32(sbase + st * stage_bytes) >> 4);
+          const uint32_t dy_lo = lbo_f | (w_smem_u32(sbase + st * stage_bytes + DY_PLANE) >> 4);
+          const uint32_t x_hi = lbo_f | (w_smem_u32(sbase + st * stage_bytes + NPL * DY_PLANE) >> 4);
+          const uint32_t x_lo = lbo_f | (w_smem_u32(sbase + st * stage_bytes + NPL * DY_PLANE + x_plane) >> 4);
+          for (int t = t0; t < t1; ++t) {
+            const uint32_t xo = (uint32_t)(p.tapoff[t] - minoff);          // rows are 16 B: row offset == 16-byte units
+            const uint32_t d = tmem_base + (uint32_t)((t - t0) * NCI);
 #pragma unroll
-          for (int kk = 0; kk < KT / 16; ++kk) {
-            const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
-            // MN-major SWIZZLE_NONE: LBO = 128 B (next 8 K rows), SBO = chunk pitch (next 8 M/N channels)
-            const uint64_t ah = w_desc(dy_hi + kk * 256, 128u, DY_PITCH);
-            const uint64_t bh = w_desc(x_hi + xoff + kk * 256, 128u, (uint32_t)p.xpitch_b);
-            if (PREC == 3) {
-              const uint64_t al = w_desc(dy_lo + kk * 256, 128u, DY_PITCH);
-              const uint64_t bl = w_desc(x_lo + xoff + kk * 256, 128u, (uint32_t)p.xpitch_b);
-              w_umma(d, al, bh, idesc, acc);
-              w_umma(d, ah, bl, idesc, 1u);
-              w_umma(d, ah, bh, idesc, 1u);
-            } else {
-              w_umma(d, ah, bh, idesc, acc);
+            for (int kk = 0; kk < KT / 16; ++kk) {
+              const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
+              const uint32_t ko = (uint32_t)kk * 16u;                       // 16 pixel rows = 256 B
+              auto mma = [&](uint32_t alo, uint32_t blo, uint32_t accf) {
+                asm volatile(
+                    "{\n.reg .pred p;\n.reg .b64 da, db;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\nsetp.ne.b32 p, %6, 0;\n"
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}\n" ::"r"(d), "r"(alo), "r"(a_hi32), "r"(blo), "r"(b_hi32),
+                    "r"(idesc), "r"(accf)
+                    : "memory");
+              };
+              if (PREC == 3) {
+                mma(dy_lo + ko, x_hi + xo + ko, acc);
+                mma(dy_hi + ko, x_lo + xo + ko, 1u);
+                mma(dy_hi + ko, x_hi + xo + ko, 1u);
+              } else {
+                mma(dy_hi + ko, x_hi + xo + ko, acc);
+              }
             }
           }
+          w_commit(empty(st));
         }
-        w_commit(empty(st));
+        __syncwarp();
       }
-      w_commit(accFull);
+      if (leader) w_commit(accFull);
+      __syncwarp();
     }
-    __syncwarp();
   }
   __syncthreads();
   if (warp == kWProdWarps) {

@@ -30,13 +30,9 @@ def run(n, cin, cout, h, k, msub=0, affine=True, prec=3, nt256=1):
     pv = prof.cpu().tolist()
     print(f'conv {cin}->{cout} {k}x{k} @{h}px n={n} msub={msub} prec={prec} nt256={nt256}: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s')
     print('   ' + '  '.join(f'{a}={b}' for a, b in zip(names, pv)))
-for nt in (0, 1):
-    for ms in (1, 2):
-        run(64, 256, 256, 32, 3, msub=ms, nt256=nt)
-run(64, 256, 256, 16, 3, msub=1, nt256=0)
-run(64, 256, 256, 16, 3, msub=1, nt256=1)
-run(64, 256, 256, 16, 3, msub=2, nt256=1)
-run(64, 256, 768, 16, 1, nt256=0)
-run(64, 256, 768, 16, 1, nt256=1)
-run(64, 256, 256, 8, 3, nt256=0)
+run(64, 256, 256, 4, 3, nt256=3)
+run(64, 256, 256, 4, 3, nt256=1)
+run(64, 256, 256, 4, 3, nt256=1, affine=False)
+run(64, 256, 256, 8, 3, nt256=3)
 run(64, 256, 256, 8, 3, nt256=1)
+run(64, 512, 512, 4, 3, nt256=1)
