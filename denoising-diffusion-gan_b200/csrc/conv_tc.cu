@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   }
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(fullA(s), kProdWarps * 32); mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(fullA(s), kProdWarps); mbar_init(emptyA(s), 1); }
     for (int s = 0; s < NSB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
     mbar_init(accFull, 1);
     fence_barrier_init();
@@ -458,7 +458,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         transform_store(S, v, off >= 0, nn, ch0, cur_n, sc, sh, dst_hi, dst_lo, e);
       }
       fence_proxy_async();
-      mbar_arrive(fullA(st));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(fullA(st));       // one arrival per warp: 256 serialized arrivals cost more than the copy
       // ---- rotate the register pipeline ----
       if (has_next) {
 #pragma unroll
@@ -781,7 +782,7 @@ static int pick_nt(int cout, long m_rows) {
   if (cout <= 64) return 64;
   if (g_nt256 && cout % 256 == 0 && ((m_rows + 127) / 128) * (cout / 256) >= 148) return 256;
   // tiny spatial levels (4x4, 8x8): narrow tiles multiply the CTA count and shorten each CTA's serial MMA chain
-  if (g_small_nt64 && cout % 64 == 0 && ((m_rows + 127) / 128) * ((cout + 127) / 128) < 100) return 64;
+  if (g_small_nt64 && cout % 64 == 0 && ((m_rows + 127) / 128) * (cout / 64) <= 148) return 64;
   return 128;
 }
 static bool valid_nt(int nt) { return nt == 16 || nt == 64 || nt == 128 || nt == 256; }
@@ -932,7 +933,7 @@ extern "C" int ddg_conv2d_fwd(const ddg_conv_desc* c, cudaStream_t stream) {
     d.win_rows = window ? MT + 2 * d.margin : MT;
   }
   int rows = d.win_rows;
-  if ((rows & 1) == 0) rows += 1;                   // odd pitch (in 16-byte units): conflict-free chunk-strided stores
+  rows += (10 - (rows & 7)) & 7;                    // pitch = 32 (mod 128) bytes: the 4 chunks x 2 rows of a 16-byte store phase hit 8 distinct bank groups
   d.win_pitch = rows * 16;
   const int prec = c->precision == 1 ? 1 : 3;
 

@@ -90,6 +90,16 @@ class _EngineBase:
         self.conv_flops += 2 * n * hout * wout * cout * sum(s['C'] * len(s['taps']) for s in srcs)
         return cw
 
+    def _linear_rows(self, x, k, w, b, out, act_in=ops.ACT_NONE):
+        """out[N][J] = act_in(x[N][k]) @ w[J][k]^T + b as one tensor-core GEMM (rows = batch samples); w is re-packed by a binder
+        that must run after whatever fills w.  Falls back to the SIMT linear kernel when k is not a multiple of the K block."""
+        j = w.shape[0]
+        if k % ops.KB != 0:
+            self._step(lambda: ops.linear(x, w, b, act_in=act_in, out=out))
+            return
+        self._conv(j, [ops.conv_src(x, k, ops.TAPS_1X1, act=act_in, padded=False)], 1, 1, out,
+                   lambda cw: cw.pack_segment(0, w, k, k, 1, 0), out_mode=ops.OUT_NHWC, bias=b)
+
     def _gn_coeffs(self, acts, groups, gamma, beta, gb_stride, per_sample, eps=1e-6):
         """scale/shift [N][C] of the GroupNorm over the channel concatenation of `acts` (ncsnpp...:367 torch.cat)."""
         c = sum(a.C for a in acts)
@@ -206,8 +216,8 @@ class GeneratorEngine(_EngineBase):
         self._step(lambda: ops.timestep_embedding(self.t_in, nf, out=temb0))
         self._step(lambda: ops.linear(temb0, P['all_modules.0.weight'], P['all_modules.0.bias'], out=temb1))
         self._step(lambda: ops.linear(temb1, P['all_modules.1.weight'], P['all_modules.1.bias'], act_in=ops.ACT_SILU, out=self.temb))
-        self._step(lambda: ops.linear(self.zemb, self._w_style, self._b_style, out=self.style_all))
-        self._step(lambda: ops.linear(self.temb, self._w_dense, self._b_dense, act_in=ops.ACT_SILU, out=self.dense_all))
+        self._linear_rows(self.zemb, zd, self._w_style, self._b_style, self.style_all)
+        self._linear_rows(self.temb, 4 * nf, self._w_dense, self._b_dense, self.dense_all, act_in=ops.ACT_SILU)
         self._keep.append((zb, temb0, temb1))
 
         # input image -> PNHWC (channels padded to 32); "2x-1" when data is not centered (:308-310)
@@ -465,7 +475,7 @@ class DiscriminatorEngine(_EngineBase):
                 w_dense[offs[i]:offs[i] + b].copy_(P[f'conv{i + 1}.dense_t1.weight'])
                 b_dense[offs[i]:offs[i] + b].copy_(P[f'conv{i + 1}.dense_t1.bias'])
         self.binders.append(bind_dense)
-        self._step(lambda: ops.linear(te, w_dense, b_dense, act_in=ops.ACT_LEAKY, out=self.dense_all))
+        self._linear_rows(te, te_dim, w_dense, b_dense, self.dense_all, act_in=ops.ACT_LEAKY)
         self._keep.append((te0, te1, te, w_dense, b_dense))
         # input: cat(x, x_t) (:138) -> PNHWC
         cp_in = ops.pad_c(self.nc)

@@ -45,3 +45,15 @@ for n, (c, t) in rows[:45]:
         fl = 2 * B * h * w * cout * k
         extra = f'  {fl / (t / c * 1e-3) / 1e12:7.1f} TFLOP/s/launch'
     print(f'{t:8.3f} ms ({100 * t / tot:5.1f}%) x{c:2d}  {n}{extra}')
+cat = collections.OrderedDict()
+for n, (c, t) in agg.items():
+    if n.startswith('conv'):
+        m = re.search(r'(\d+)x(\d+) srcs=(.*)', n)
+        taps = [b for a, b in eval(m.group(3))]
+        key = f'conv {m.group(1)}px ' + ('3x3' if taps == [9] or taps == [9, 9] else ('3x3+1x1' if 9 in taps else '1x1/other'))
+    else:
+        key = n.split(':')[0]
+    cat.setdefault(key, [0, 0.0]); cat[key][0] += c; cat[key][1] += t
+print('--- categories ---')
+for k, (c, t) in sorted(cat.items(), key=lambda kv: -kv[1][1]):
+    print(f'{t:8.3f} ms ({100 * t / tot:5.1f}%) x{c:3d}  {k}')

@@ -5,7 +5,7 @@ import torch
 from ddgan_b200 import ops
 dev = 'cuda'
 names = ['prod_total', 'prod_wait_emptyA', 'prod_wait_acc', 'epilogue', 'loader_total', 'loader_wait_emptyB', 'mma_total', 'mma_wait_A', 'mma_wait_B']
-def run(n, cin, cout, h, k, msub=0, affine=True, prec=3, nt256=1):
+def run(n, cin, cout, h, k, msub=0, affine=True, prec=3, nt256=1, stats=True):
     from ddgan_b200._lib import lib
     lib().ddg_conv_set_nt256(nt256)
     cp = ops.pad_c(cin)
@@ -17,7 +17,7 @@ def run(n, cin, cout, h, k, msub=0, affine=True, prec=3, nt256=1):
     out = ops.alloc_pnhwc(n, h, h, cout, dev)
     st = torch.zeros(n, cout, 2, dtype=torch.float64, device=dev)
     prof = torch.zeros(16, dtype=torch.int64, device=dev)
-    d = ops.build_conv_desc(cw, [ops.conv_src(x, cp, taps, scale=sc, shift=sh, act=1 if affine else 0)], n, h, h, out, stats=st, msub=msub, prof=prof,
+    d = ops.build_conv_desc(cw, [ops.conv_src(x, cp, taps, scale=sc, shift=sh, act=1 if affine else 0)], n, h, h, out, stats=st if stats else None, msub=msub, prof=prof,
                             bias=torch.zeros(cout, device=dev))
     for _ in range(3): ops.conv_launch(d)
     torch.cuda.synchronize()
@@ -28,11 +28,11 @@ def run(n, cin, cout, h, k, msub=0, affine=True, prec=3, nt256=1):
     ms = e0.elapsed_time(e1) / 10
     fl = 2 * n * h * h * cout * cp * k * k
     pv = prof.cpu().tolist()
-    print(f'conv {cin}->{cout} {k}x{k} @{h}px n={n} msub={msub} prec={prec} nt256={nt256}: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s')
+    print(f'conv {cin}->{cout} {k}x{k} @{h}px n={n} msub={msub} prec={prec} nt256={nt256} stats={stats}: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s')
     print('   ' + '  '.join(f'{a}={b}' for a, b in zip(names, pv)))
-run(64, 256, 256, 4, 3, nt256=3)
-run(64, 256, 256, 4, 3, nt256=1)
-run(64, 256, 256, 4, 3, nt256=1, affine=False)
+run(64, 128, 128, 32, 3)
+run(64, 128, 128, 32, 3, stats=False)
+run(64, 256, 256, 16, 3)
+run(64, 256, 256, 16, 3, stats=False)
+run(64, 256, 256, 8, 3)
 run(64, 256, 256, 8, 3, nt256=3)
-run(64, 256, 256, 8, 3, nt256=1)
-run(64, 512, 512, 4, 3, nt256=1)
