@@ -21,6 +21,7 @@
 //     tcgen05.mma.cta_group::1.kind::f16; tcgen05.commit releases the smem stages and signals the epilogue.
 //   * Epilogue: tcgen05.ld -> + bias[c] + addvec[n,c] -> (+ residual) * out_scale -> act -> store (padded NHWC /
 //     NHWC / NCHW) and per-(n,c) sum / sum-of-squares accumulation for the GroupNorm that consumes the output.
+#include <cstdlib>
 #include "common.cuh"
 #include "ddgan_b200.h"
 
@@ -193,11 +194,17 @@ struct ConvDev {
   int sub_stride;              // byte distance between the two 128-row sub-tiles inside the A window
   long long* prof;             // optional: per-role cycle counters of CTA (0,0) (bring-up / tuning aid)
   int batch_rows;              // >0: batched GEMM mode (gather only): blockIdx.z = batch, rows per batch
+  int tiles_m, n_tiles;        // persistent variant: tile = n_tile * tiles_m + m_tile, CTA b runs tiles b, b + grid, ...
   long w_batch_stride;         // bytes between the packed B operands of consecutive batches
 };
 
 constexpr int kProdWarps = 8;
-constexpr int kThreads = (kProdWarps + 2) * 32;
+constexpr int kThreads = (kProdWarps + 2) * 32;   // one tile per CTA: the producer warps also run the epilogue
+// Persistent variant: 4 warpgroups.  WG0-1 = A producers, WG2 = {B loader, MMA issuer, 2 idle warps}, WG3 = epilogue warps
+// (warp % 4 = TMEM lane quadrant).  Registers are moved from WG2 to the producers with setmaxnreg.
+constexpr int kThreadsPersist = 16 * 32;
+constexpr int kEpiWarp0 = 12;
+constexpr int kRegsProd = 168, kRegsUtil = 40, kRegsEpi = 128;   // 256*168 + 128*40 + 128*128 = 64512 <= 65536
 
 template <int MSUB, int NT, int KB, int PREC>
 struct ConvCfg {
@@ -231,9 +238,12 @@ __device__ __forceinline__ void decode_out_row(const ConvDev& p, int m, int m_en
   if (n >= p.N) n = p.N - 1;
 }
 
-template <int MSUB, int NT, int KB, int PREC>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvDev p) {
+template <int MSUB, int NT, int KB, int PREC, bool PERSIST>
+__global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvDev p) {
   using Cfg = ConvCfg<MSUB, NT, KB, PREC>;
+  constexpr int ACC_COLS = MSUB * NT;                                   // TMEM columns of one accumulator set
+  constexpr int TM_COLS = PERSIST ? 2 * Cfg::TMEM_COLS : Cfg::TMEM_COLS;  // persistent: two sets, epilogue(i) overlaps mainloop(i+1)
+  static_assert(TM_COLS <= 512, "accumulators exceed TMEM");
   constexpr int MT = Cfg::MT;
   constexpr int KCH = Cfg::KCH;
   constexpr int NPL = Cfg::NPL;
@@ -247,8 +257,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   auto emptyA = [&](int s) { return bar_base + 8u * (2 + s); };
   auto fullB = [&](int s) { return bar_base + 8u * (4 + s); };
   auto emptyB = [&](int s) { return bar_base + 8u * (4 + NSB + s); };
-  const uint32_t accFull = bar_base + 8u * (4 + 2 * NSB);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (5 + 2 * NSB));
+  auto accFull = [&](int b) { return bar_base + 8u * (4 + 2 * NSB + b); };
+  auto accEmpty = [&](int b) { return bar_base + 8u * (6 + 2 * NSB + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (8 + 2 * NSB));
   uint8_t* sB = smem + 256;
   const int a_plane = KCH * p.win_pitch;          // bytes of one A plane
   const int a_stage = a_plane * NPL;
@@ -256,28 +267,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = (p.batch_rows > 0 ? blockIdx.z * p.batch_rows : 0) + blockIdx.x * MT;
-  const int m_end = p.batch_rows > 0 ? (blockIdx.z + 1) * p.batch_rows : p.Mtotal;
-  const int ntile = blockIdx.y;
+  // Tile loop: the persistent variant walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; otherwise the CTA owns one tile.
+  const int tile_first = PERSIST ? (int)blockIdx.x : 0;
+  const int tile_stride = PERSIST ? (int)gridDim.x : 1;
+  const int tile_end = PERSIST ? p.tiles_m * p.n_tiles : 1;
+  int m0 = 0, m_end = p.Mtotal, ntile = 0;
   // 2-D tile geometry: 8 columns wide so that every image row of the tile is exactly one 8-row UMMA core-matrix group; the
   // A operand is then uniformly strided (SBO = 10 entries) inside a (rows+2) x 10 halo window and a tap is still an offset.
   int t2_n = 0, t2_y0 = 0, t2_x0 = 0;
-  if (p.tile2d) {
-    const int tx = blockIdx.x % p.tiles_x;
-    const int r_ = blockIdx.x / p.tiles_x;
-    t2_n = r_ / p.tiles_y;
-    t2_y0 = (r_ - t2_n * p.tiles_y) * 16 * MSUB;
-    t2_x0 = tx * 8;
-  }
+  auto set_tile = [&](int tile) {
+    int mx;
+    if (PERSIST) { ntile = tile / p.tiles_m; mx = tile - ntile * p.tiles_m; }
+    else { mx = blockIdx.x; ntile = blockIdx.y; }
+    m0 = (p.batch_rows > 0 ? blockIdx.z * p.batch_rows : 0) + mx * MT;
+    m_end = p.batch_rows > 0 ? (blockIdx.z + 1) * p.batch_rows : p.Mtotal;
+    if (p.tile2d) {
+      const int tx = mx % p.tiles_x;
+      const int r_ = mx / p.tiles_x;
+      t2_n = r_ / p.tiles_y;
+      t2_y0 = (r_ - t2_n * p.tiles_y) * 16 * MSUB;
+      t2_x0 = tx * 8;
+    }
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(fullA(s), kProdWarps); mbar_init(emptyA(s), 1); }
     for (int s = 0; s < NSB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
-    mbar_init(accFull, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(accFull(b), 1); mbar_init(accEmpty(b), PERSIST ? 4 : kProdWarps); }
     fence_barrier_init();
   }
   if (warp == kProdWarps + 1) {
-    tmem_alloc<Cfg::TMEM_COLS>(smem_u32(tmem_slot));
+    tmem_alloc<TM_COLS>(smem_u32(tmem_slot));
   }
   tc_fence_before();
   __syncthreads();
@@ -288,218 +308,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   int nkb_total = 0;
   for (int s = 0; s < p.nsrc; ++s) nkb_total += p.src[s].C / KB;
 
-  if (warp < kProdWarps) {
-    // =================================== A producers ===================================
-    // Software-pipelined: each thread owns one 16-byte channel chunk (c) and up to IMAX window rows (e0 + k*ESTEP).
-    // Row geometry (global offset, sample index, liveness) is computed once per source; the rows of K-block i+1 are
-    // prefetched into registers while K-block i is converted and stored, so one global-load latency is exposed per
-    // K-block at most (it was one per row before: the dominant long-scoreboard stall in the first ncu capture).
-    const int tid = threadIdx.x;                     // 0..255
-    constexpr int NPT = kProdWarps * 32;
-    constexpr int ESTEP = NPT / KCH;
-    constexpr int IMAX = (MSUB == 2) ? 5 : 4;   // 320 threads cap ptxas at 168 registers: a 6th pipelined row would spill
-    const int c = tid % KCH;                         // fixed 16-byte chunk of this thread
-    const int e0 = tid / KCH;
-
-    // off >= 0: element offset of the row in the source; -1: store zeros; -2: row not part of this source's window
-    auto row_info = [&](const SrcDev& S, int e, int row_hi, int& off, int& nn) {
-      off = -2; nn = 0;
-      if (e >= row_hi) return;
-      off = -1;
-      if (p.tile2d) {
-        const int wy = e / 10, wx = e - wy * 10;
-        const int y = t2_y0 - 1 + wy, x = t2_x0 - 1 + wx;     // image coordinates; the PNHWC buffer holds the zero border
-        nn = t2_n;
-        const bool inside = (y >= 0) && (y < p.Hout) && (x >= 0) && (x < p.Wout);
-        if (y <= p.Hout && (inside || S.scale == nullptr))
-          off = ((t2_n * (p.Hout + 2) + y + 1) * (p.Wout + 2) + (x + 1)) * S.pitch;
-      } else if (p.window) {
-        const int g = m0 - p.margin + e;             // row in padded linear space
-        if (g >= 0 && g < p.Mtotal) {
-          const int img = p.Hp * p.Wp;
-          const int n = g / img;
-          bool live = true;
-          if (S.scale != nullptr) {                  // padding must stay zero after the affine prologue
-            const int r = g - n * img;
-            const int hp = r / p.Wp, wp = r - hp * p.Wp;
-            live = (hp >= 1) && (hp < p.Hp - 1) && (wp >= 1) && (wp < p.Wp - 1);
-          }
-          if (live) { off = g * S.pitch; nn = n; }
-        }
-      } else {
-        const int m = m0 + e;
-        if (m < m_end) {
-          const int img = p.Hout * p.Wout;
-          const int n = m / img;
-          nn = n;
-          if (S.padded) {
-            const int r = m - n * img;
-            const int h = r / p.Wout, w = r - h * p.Wout;
-            off = ((n * (p.Hout + 2) + h + 1) * (p.Wout + 2) + (w + 1)) * S.pitch;
-          } else {
-            off = m * S.pitch;
-          }
-        }
-      }
-    };
-    auto src_rows = [&](const SrcDev& S, int& row_lo, int& row_hi) {
-      row_lo = 0; row_hi = p.win_rows;
-      if (p.window && !p.tile2d && S.ntaps == 1) { row_lo = S.tapoff[0]; row_hi = S.tapoff[0] + MT; }
-    };
-    auto transform_store = [&](const SrcDev& S, float* v, bool live, int n, int ch0, int& cur_n, float* sc, float* sh,
-                               uint8_t* dst_hi, uint8_t* dst_lo, int e) {
-      if (live) {
-        if (S.scale != nullptr) {
-          if (n != cur_n) {
-            cur_n = n;
-            const float4* ps = reinterpret_cast<const float4*>(S.scale + (size_t)n * S.ss_stride + ch0);
-            const float4* pt = reinterpret_cast<const float4*>(S.shift + (size_t)n * S.ss_stride + ch0);
-            const float4 s0 = __ldg(ps), s1 = __ldg(ps + 1), t0 = __ldg(pt), t1 = __ldg(pt + 1);
-            sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
-            sh[0] = t0.x; sh[1] = t0.y; sh[2] = t0.z; sh[3] = t0.w; sh[4] = t1.x; sh[5] = t1.y; sh[6] = t1.z; sh[7] = t1.w;
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
-        }
-        if (S.act == ACT_SILU) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
-        } else if (S.act == ACT_LEAKY) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = leaky_f(v[j]);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = 0.f;
-      }
-      uint4 hi, lo;
-      split_bf16x2(v[0], v[1], hi.x, lo.x);
-      split_bf16x2(v[2], v[3], hi.y, lo.y);
-      split_bf16x2(v[4], v[5], hi.z, lo.z);
-      split_bf16x2(v[6], v[7], hi.w, lo.w);
-      *reinterpret_cast<uint4*>(dst_hi + e * 16) = hi;
-      if (NPL == 2) *reinterpret_cast<uint4*>(dst_lo + e * 16) = lo;
-    };
-
-    const bool prof_on = (p.prof != nullptr) && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0;
-    long long t_prod0 = clock64(), w_emptyA = 0;
-    float cur[IMAX][8], nxt[IMAX][8];
-    int off_c[IMAX], nn_c[IMAX], off_n[IMAX], nn_n[IMAX];
-    int s_cur = 0, kb_cur = 0;
-    {
-      int lo_, hi_;
-      src_rows(p.src[0], lo_, hi_);
-#pragma unroll
-      for (int k = 0; k < IMAX; ++k) {
-        row_info(p.src[0], lo_ + e0 + k * ESTEP, hi_, off_c[k], nn_c[k]);
-        if (off_c[k] >= 0) {
-          const float4* q = reinterpret_cast<const float4*>(p.src[0].x + off_c[k] + c * 8);
-          const float4 a = __ldg(q), b = __ldg(q + 1);
-          cur[k][0] = a.x; cur[k][1] = a.y; cur[k][2] = a.z; cur[k][3] = a.w;
-          cur[k][4] = b.x; cur[k][5] = b.y; cur[k][6] = b.z; cur[k][7] = b.w;
-        }
-      }
-    }
-    for (int kb_idx = 0; kb_idx < nkb_total; ++kb_idx) {
-      const SrcDev& S = p.src[s_cur];
-      // ---- prefetch the next K-block ----
-      int s_nxt = s_cur, kb_nxt = kb_cur + 1;
-      if (kb_nxt >= S.C / KB) { s_nxt = s_cur + 1; kb_nxt = 0; }
-      const bool has_next = kb_idx + 1 < nkb_total;
-      if (has_next) {
-        const SrcDev& Sn = p.src[s_nxt];
-        if (s_nxt != s_cur) {
-          int lo_, hi_;
-          src_rows(Sn, lo_, hi_);
-#pragma unroll
-          for (int k = 0; k < IMAX; ++k) row_info(Sn, lo_ + e0 + k * ESTEP, hi_, off_n[k], nn_n[k]);
-        } else {
-#pragma unroll
-          for (int k = 0; k < IMAX; ++k) { off_n[k] = off_c[k]; nn_n[k] = nn_c[k]; }
-        }
-        const int chn = kb_nxt * KB + c * 8;
-#pragma unroll
-        for (int k = 0; k < IMAX; ++k) {
-          if (off_n[k] >= 0) {
-            const float4* q = reinterpret_cast<const float4*>(Sn.x + off_n[k] + chn);
-            const float4 a = __ldg(q), b = __ldg(q + 1);
-            nxt[k][0] = a.x; nxt[k][1] = a.y; nxt[k][2] = a.z; nxt[k][3] = a.w;
-            nxt[k][4] = b.x; nxt[k][5] = b.y; nxt[k][6] = b.z; nxt[k][7] = b.w;
-          }
-        }
-      }
-      // ---- convert + store the current K-block ----
-      const int st = kb_idx & 1;
-      const uint32_t ph = (kb_idx >> 1) & 1;
-      { const long long tw = clock64(); mbar_wait(emptyA(st), ph ^ 1); w_emptyA += clock64() - tw; }
-      uint8_t* dst_hi = sA + st * a_stage + c * p.win_pitch;
-      uint8_t* dst_lo = dst_hi + a_plane;
-      const int ch0 = kb_cur * KB + c * 8;
-      int cur_n = -1;
-      float sc[8], sh[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; }
-      int row_lo, row_hi;
-      src_rows(S, row_lo, row_hi);
-#pragma unroll
-      for (int k = 0; k < IMAX; ++k) {
-        if (off_c[k] != -2) transform_store(S, cur[k], off_c[k] >= 0, nn_c[k], ch0, cur_n, sc, sh, dst_hi, dst_lo, row_lo + e0 + k * ESTEP);
-      }
-      // rows beyond the register pipeline (very wide windows only)
-      for (int e = row_lo + e0 + IMAX * ESTEP; e < row_hi; e += ESTEP) {
-        int off, nn;
-        row_info(S, e, row_hi, off, nn);
-        float v[8];
-        if (off >= 0) {
-          const float4* q = reinterpret_cast<const float4*>(S.x + off + ch0);
-          const float4 a = __ldg(q), b = __ldg(q + 1);
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        }
-        transform_store(S, v, off >= 0, nn, ch0, cur_n, sc, sh, dst_hi, dst_lo, e);
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(fullA(st));       // one arrival per warp: 256 serialized arrivals cost more than the copy
-      // ---- rotate the register pipeline ----
-      if (has_next) {
-#pragma unroll
-        for (int k = 0; k < IMAX; ++k) {
-          off_c[k] = off_n[k]; nn_c[k] = nn_n[k];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) cur[k][j] = nxt[k][j];
-        }
-        s_cur = s_nxt; kb_cur = kb_nxt;
-      }
-    }
-
-    // =================================== epilogue ===================================
-    const long long t_prod1 = clock64();
-    mbar_wait(accFull, 0);
-    const long long t_epi0 = clock64();
+  // =================================== epilogue (one tile) ===================================
+  // quad: TMEM lane quadrant of the calling warp; the warp handles column chunks half0, half0 + hstep, ...
+  // it: tile iteration of this CTA (selects the accumulator set and the barrier parity).
+  auto run_epilogue = [&](int it, int quad, int half0, int hstep, bool release) {
+    const int ab = PERSIST ? (it & 1) : 0;
+    mbar_wait(accFull(ab), PERSIST ? ((it >> 1) & 1) : 0);
     tc_fence_after();
-    const int quad = warp & 3;                       // TMEM lane quadrant accessible by this warp
-    const int half = warp >> 2;                      // column half handled by this warp
     constexpr int CW = (NT >= 64) ? 32 : 16;         // columns per tcgen05.ld
     constexpr int NCHUNK = NT / CW;
-    for (int sub = 0; sub < MSUB; ++sub) {
-      const int m = m0 + sub * 128 + quad * 32 + lane;
-      bool valid; int n, h, w;
-      if (p.tile2d) {
-        const int ml = sub * 128 + quad * 32 + lane;
-        n = t2_n; h = t2_y0 + (ml >> 3); w = t2_x0 + (ml & 7);
-        valid = (h < p.Hout) && (w < p.Wout);
-      } else {
-        decode_out_row(p, m, m_end, valid, n, h, w);
-      }
-      size_t obase = 0;
-      if (p.out_mode == 0) obase = ((size_t)(n * (p.Hout + 2) + h + 1) * (p.Wout + 2) + (w + 1)) * p.out_C;
-      else if (p.out_mode == 1) obase = ((size_t)(n * p.Hout + h) * p.Wout + w) * p.out_C;
-      const int n_first = __shfl_sync(0xffffffffu, n, 0);
-      const int n_last = __shfl_sync(0xffffffffu, n, 31);
-      for (int ck = half; ck < NCHUNK; ck += 2) {
+    // work units = (sub-tile, column chunk) pairs, dealt round-robin to the warps that share this lane quadrant
+    int sub_prev = -1;
+    bool valid = false; int n = 0, h = 0, w = 0;
+    size_t obase = 0;
+    int n_first = 0, n_last = 0;
+    {
+      for (int u = half0; u < MSUB * NCHUNK; u += hstep) {
+        const int sub = u / NCHUNK, ck = u - sub * NCHUNK;
+        if (sub != sub_prev) {
+          sub_prev = sub;
+          const int m = m0 + sub * 128 + quad * 32 + lane;
+          if (p.tile2d) {
+            const int ml = sub * 128 + quad * 32 + lane;
+            n = t2_n; h = t2_y0 + (ml >> 3); w = t2_x0 + (ml & 7);
+            valid = (h < p.Hout) && (w < p.Wout);
+          } else {
+            decode_out_row(p, m, m_end, valid, n, h, w);
+          }
+          obase = 0;
+          if (p.out_mode == 0) obase = ((size_t)(n * (p.Hout + 2) + h + 1) * (p.Wout + 2) + (w + 1)) * p.out_C;
+          else if (p.out_mode == 1) obase = ((size_t)(n * p.Hout + h) * p.Wout + w) * p.out_C;
+          n_first = __shfl_sync(0xffffffffu, n, 0);
+          n_last = __shfl_sync(0xffffffffu, n, 31);
+        }
         const int col0 = ntile * NT + ck * CW;
         float v[CW];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(sub * NT + ck * CW);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * ACC_COLS + sub * NT + ck * CW);
         if (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
         tmem_ld_wait();
         if (col0 < p.Cout) {
@@ -611,26 +455,240 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
       }
     }
+    // accumulator set drained: hand it back to the MMA issuer
     tc_fence_before();
-    if (prof_on && tid == 0) {
-      p.prof[0] = t_prod1 - t_prod0;   // producer loop total
-      p.prof[1] = w_emptyA;            // ... of which waiting for a free A stage
-      p.prof[2] = t_epi0 - t_prod1;    // waiting for the accumulator after the last A stage
-      p.prof[3] = clock64() - t_epi0;  // epilogue
+    __syncwarp();
+    if (release && lane == 0) mbar_arrive(accEmpty(ab));
+  };
+
+  if (warp < kProdWarps) {
+    // =================================== A producers ===================================
+    // Software-pipelined: each thread owns one 16-byte channel chunk (c) and up to IMAX window rows (e0 + k*ESTEP).
+    // Row geometry (global offset, sample index, liveness) is computed once per source; the rows of K-block i+1 are
+    // prefetched into registers while K-block i is converted and stored, so one global-load latency is exposed per
+    // K-block at most (it was one per row before: the dominant long-scoreboard stall in the first ncu capture).
+    const int tid = threadIdx.x;                     // 0..255
+    constexpr int NPT = kProdWarps * 32;
+    constexpr int ESTEP = NPT / KCH;
+    constexpr int IMAX = (MSUB == 2) ? 5 : 4;   // 320 threads cap ptxas at 168 registers: a 6th pipelined row would spill
+    const int c = tid % KCH;                         // fixed 16-byte chunk of this thread
+    const int e0 = tid / KCH;
+
+    // off >= 0: element offset of the row in the source; -1: store zeros; -2: row not part of this source's window
+    auto row_info = [&](const SrcDev& S, int e, int row_hi, int& off, int& nn) {
+      off = -2; nn = 0;
+      if (e >= row_hi) return;
+      off = -1;
+      if (p.tile2d) {
+        const int wy = e / 10, wx = e - wy * 10;
+        const int y = t2_y0 - 1 + wy, x = t2_x0 - 1 + wx;     // image coordinates; the PNHWC buffer holds the zero border
+        nn = t2_n;
+        const bool inside = (y >= 0) && (y < p.Hout) && (x >= 0) && (x < p.Wout);
+        if (y <= p.Hout && (inside || S.scale == nullptr))
+          off = ((t2_n * (p.Hout + 2) + y + 1) * (p.Wout + 2) + (x + 1)) * S.pitch;
+      } else if (p.window) {
+        const int g = m0 - p.margin + e;             // row in padded linear space
+        if (g >= 0 && g < p.Mtotal) {
+          const int img = p.Hp * p.Wp;
+          const int n = g / img;
+          bool live = true;
+          if (S.scale != nullptr) {                  // padding must stay zero after the affine prologue
+            const int r = g - n * img;
+            const int hp = r / p.Wp, wp = r - hp * p.Wp;
+            live = (hp >= 1) && (hp < p.Hp - 1) && (wp >= 1) && (wp < p.Wp - 1);
+          }
+          if (live) { off = g * S.pitch; nn = n; }
+        }
+      } else {
+        const int m = m0 + e;
+        if (m < m_end) {
+          const int img = p.Hout * p.Wout;
+          const int n = m / img;
+          nn = n;
+          if (S.padded) {
+            const int r = m - n * img;
+            const int h = r / p.Wout, w = r - h * p.Wout;
+            off = ((n * (p.Hout + 2) + h + 1) * (p.Wout + 2) + (w + 1)) * S.pitch;
+          } else {
+            off = m * S.pitch;
+          }
+        }
+      }
+    };
+    auto src_rows = [&](const SrcDev& S, int& row_lo, int& row_hi) {
+      row_lo = 0; row_hi = p.win_rows;
+      if (p.window && !p.tile2d && S.ntaps == 1) { row_lo = S.tapoff[0]; row_hi = S.tapoff[0] + MT; }
+    };
+    auto transform_store = [&](const SrcDev& S, float* v, bool live, int n, int ch0, int& cur_n, float* sc, float* sh,
+                               uint8_t* dst_hi, uint8_t* dst_lo, int e) {
+      if (live) {
+        if (S.scale != nullptr) {
+          if (n != cur_n) {
+            cur_n = n;
+            const float4* ps = reinterpret_cast<const float4*>(S.scale + (size_t)n * S.ss_stride + ch0);
+            const float4* pt = reinterpret_cast<const float4*>(S.shift + (size_t)n * S.ss_stride + ch0);
+            const float4 s0 = __ldg(ps), s1 = __ldg(ps + 1), t0 = __ldg(pt), t1 = __ldg(pt + 1);
+            sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+            sh[0] = t0.x; sh[1] = t0.y; sh[2] = t0.z; sh[3] = t0.w; sh[4] = t1.x; sh[5] = t1.y; sh[6] = t1.z; sh[7] = t1.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+        }
+        if (S.act == ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+        } else if (S.act == ACT_LEAKY) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = leaky_f(v[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      }
+      uint4 hi, lo;
+      split_bf16x2(v[0], v[1], hi.x, lo.x);
+      split_bf16x2(v[2], v[3], hi.y, lo.y);
+      split_bf16x2(v[4], v[5], hi.z, lo.z);
+      split_bf16x2(v[6], v[7], hi.w, lo.w);
+      *reinterpret_cast<uint4*>(dst_hi + e * 16) = hi;
+      if (NPL == 2) *reinterpret_cast<uint4*>(dst_lo + e * 16) = lo;
+    };
+
+    if (PERSIST) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsProd));
+    uint32_t ga = 0;                                   // A stages produced so far (ring position / parity across tiles)
+    int it = 0;
+    bool prof_on = false;
+    long long t_prod0 = 0, w_emptyA = 0;
+    for (int tile = tile_first; tile < tile_end; tile += tile_stride, ++it) {
+      set_tile(tile);
+      prof_on = (p.prof != nullptr) && it == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0;
+      t_prod0 = clock64();
+    float cur[IMAX][8], nxt[IMAX][8];
+    int off_c[IMAX], nn_c[IMAX], off_n[IMAX], nn_n[IMAX];
+    int s_cur = 0, kb_cur = 0;
+    {
+      int lo_, hi_;
+      src_rows(p.src[0], lo_, hi_);
+#pragma unroll
+      for (int k = 0; k < IMAX; ++k) {
+        row_info(p.src[0], lo_ + e0 + k * ESTEP, hi_, off_c[k], nn_c[k]);
+        if (off_c[k] >= 0) {
+          const float4* q = reinterpret_cast<const float4*>(p.src[0].x + off_c[k] + c * 8);
+          const float4 a = __ldg(q), b = __ldg(q + 1);
+          cur[k][0] = a.x; cur[k][1] = a.y; cur[k][2] = a.z; cur[k][3] = a.w;
+          cur[k][4] = b.x; cur[k][5] = b.y; cur[k][6] = b.z; cur[k][7] = b.w;
+        }
+      }
     }
-  } else if (warp == kProdWarps) {
+    for (int kb_idx = 0; kb_idx < nkb_total; ++kb_idx) {
+      const SrcDev& S = p.src[s_cur];
+      // ---- prefetch the next K-block ----
+      int s_nxt = s_cur, kb_nxt = kb_cur + 1;
+      if (kb_nxt >= S.C / KB) { s_nxt = s_cur + 1; kb_nxt = 0; }
+      const bool has_next = kb_idx + 1 < nkb_total;
+      if (has_next) {
+        const SrcDev& Sn = p.src[s_nxt];
+        if (s_nxt != s_cur) {
+          int lo_, hi_;
+          src_rows(Sn, lo_, hi_);
+#pragma unroll
+          for (int k = 0; k < IMAX; ++k) row_info(Sn, lo_ + e0 + k * ESTEP, hi_, off_n[k], nn_n[k]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < IMAX; ++k) { off_n[k] = off_c[k]; nn_n[k] = nn_c[k]; }
+        }
+        const int chn = kb_nxt * KB + c * 8;
+#pragma unroll
+        for (int k = 0; k < IMAX; ++k) {
+          if (off_n[k] >= 0) {
+            const float4* q = reinterpret_cast<const float4*>(Sn.x + off_n[k] + chn);
+            const float4 a = __ldg(q), b = __ldg(q + 1);
+            nxt[k][0] = a.x; nxt[k][1] = a.y; nxt[k][2] = a.z; nxt[k][3] = a.w;
+            nxt[k][4] = b.x; nxt[k][5] = b.y; nxt[k][6] = b.z; nxt[k][7] = b.w;
+          }
+        }
+      }
+      // ---- convert + store the current K-block ----
+      const int st = ga & 1;
+      const uint32_t ph = (ga >> 1) & 1;
+      ++ga;
+      { const long long tw = clock64(); mbar_wait(emptyA(st), ph ^ 1); w_emptyA += clock64() - tw; }
+      uint8_t* dst_hi = sA + st * a_stage + c * p.win_pitch;
+      uint8_t* dst_lo = dst_hi + a_plane;
+      const int ch0 = kb_cur * KB + c * 8;
+      int cur_n = -1;
+      float sc[8], sh[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; }
+      int row_lo, row_hi;
+      src_rows(S, row_lo, row_hi);
+#pragma unroll
+      for (int k = 0; k < IMAX; ++k) {
+        if (off_c[k] != -2) transform_store(S, cur[k], off_c[k] >= 0, nn_c[k], ch0, cur_n, sc, sh, dst_hi, dst_lo, row_lo + e0 + k * ESTEP);
+      }
+      // rows beyond the register pipeline (very wide windows only)
+      for (int e = row_lo + e0 + IMAX * ESTEP; e < row_hi; e += ESTEP) {
+        int off, nn;
+        row_info(S, e, row_hi, off, nn);
+        float v[8];
+        if (off >= 0) {
+          const float4* q = reinterpret_cast<const float4*>(S.x + off + ch0);
+          const float4 a = __ldg(q), b = __ldg(q + 1);
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        }
+        transform_store(S, v, off >= 0, nn, ch0, cur_n, sc, sh, dst_hi, dst_lo, e);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(fullA(st));       // one arrival per warp: 256 serialized arrivals cost more than the copy
+      // ---- rotate the register pipeline ----
+      if (has_next) {
+#pragma unroll
+        for (int k = 0; k < IMAX; ++k) {
+          off_c[k] = off_n[k]; nn_c[k] = nn_n[k];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cur[k][j] = nxt[k][j];
+        }
+        s_cur = s_nxt; kb_cur = kb_nxt;
+      }
+    }
+
+    }
+    if (!PERSIST) {
+      const long long t_prod1 = clock64();
+      mbar_wait(accFull(0), 0);
+      const long long t_epi0 = clock64();
+      run_epilogue(0, warp & 3, warp >> 2, 2, true);
+      if (prof_on && tid == 0) {
+        p.prof[0] = t_prod1 - t_prod0;   // producer loop total
+        p.prof[1] = w_emptyA;            // ... of which waiting for a free A stage
+        p.prof[2] = t_epi0 - t_prod1;    // waiting for the accumulator after the last A stage
+        p.prof[3] = clock64() - t_epi0;  // epilogue
+      }
+    }
+    // last tile of a persistent CTA: nothing is left to produce, so the producer warps take two thirds of its epilogue
+    // (outside the tile loop: the register pipeline of the producer loop is dead here)
+    if (PERSIST && it > 0) run_epilogue(it - 1, warp & 3, 1 + (warp >> 2), 3, false);
+  } else if (warp < kEpiWarp0) {
+    // WG2: the two single-thread roles (+ two idle warps in the persistent layout); their registers go to the producers
+    if (PERSIST) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsUtil));
+    if (warp == kProdWarps) {
     // =================================== weight loader (TMA bulk) ===================================
     if (lane == 0) {
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)ntile * p.total_stages * Cfg::B_STAGE +
-                            (p.batch_rows > 0 ? (size_t)blockIdx.z * p.w_batch_stride : 0);
       long long w_emptyB = 0;
       const long long t_l0 = clock64();
-      for (int i = 0; i < p.total_stages; ++i) {
-        const int st = i % NSB;
-        const uint32_t ph = (i / NSB) & 1;
-        { const long long tw = clock64(); mbar_wait(emptyB(st), ph ^ 1); w_emptyB += clock64() - tw; }
-        mbar_arrive_expect_tx(fullB(st), Cfg::B_STAGE);
-        tma_bulk_g2s(smem_u32(sB + st * Cfg::B_STAGE), wsrc + (size_t)i * Cfg::B_STAGE, Cfg::B_STAGE, fullB(st));
+      uint32_t gb = 0;                                 // B stages issued so far (ring position / parity across tiles)
+      for (int tile = tile_first; tile < tile_end; tile += tile_stride) {
+        set_tile(tile);
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)ntile * p.total_stages * Cfg::B_STAGE +
+                              (p.batch_rows > 0 ? (size_t)blockIdx.z * p.w_batch_stride : 0);
+        for (int i = 0; i < p.total_stages; ++i, ++gb) {
+          const int st = gb % NSB;
+          const uint32_t ph = (gb / NSB) & 1;
+          { const long long tw = clock64(); mbar_wait(emptyB(st), ph ^ 1); w_emptyB += clock64() - tw; }
+          mbar_arrive_expect_tx(fullB(st), Cfg::B_STAGE);
+          tma_bulk_g2s(smem_u32(sB + st * Cfg::B_STAGE), wsrc + (size_t)i * Cfg::B_STAGE, Cfg::B_STAGE, fullB(st));
+        }
       }
       if (p.prof != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) {
         p.prof[4] = clock64() - t_l0;  // loader loop total
@@ -638,7 +696,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
     __syncwarp();
-  } else {
+    } else if (warp == kProdWarps + 1) {
     // =================================== MMA issuer ===================================
     // The whole warp stays converged (all lanes wait on the barriers); one elected lane issues.  The first version ran this loop
     // inside `if (lane == 0)`, rebuilt four 64-bit descriptors per MMA triple and paid compiler-inserted elect / R2UR sequences
@@ -655,15 +713,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t a_kk16 = (2u * (uint32_t)p.win_pitch) >> 4;                      // +16 channels, in 16-byte units
       constexpr uint32_t b_kk16 = (2u * NT * 16u) >> 4;
       const uint32_t a_sub16 = (uint32_t)p.sub_stride >> 4;
-      int bi = 0;
-      uint32_t acc = 0;
+      uint32_t bi = 0, ga = 0;                         // B / A stages consumed so far (ring positions across tiles)
       long long w_fullA = 0, w_fullB = 0;
       const long long t_m0 = clock64();
+      int it = 0;
+      for (int tile = tile_first; tile < tile_end; tile += tile_stride, ++it) {
+      const int ab = PERSIST ? (it & 1) : 0;
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(ab * ACC_COLS);
+      // the epilogue of the tile that used this accumulator set two iterations ago must have drained it
+      mbar_wait(accEmpty(ab), (PERSIST ? ((it >> 1) & 1) : 0) ^ 1);
+      tc_fence_after();
+      uint32_t acc = 0;
       int s_m = 0, kb_m = 0;
-      for (int kb_idx = 0; kb_idx < nkb_total; ++kb_idx) {
+      for (int kb_idx = 0; kb_idx < nkb_total; ++kb_idx, ++ga) {
         const SrcDev& S = p.src[s_m];
-        const int stA = kb_idx & 1;
-        { const long long tw = clock64(); mbar_wait(fullA(stA), (kb_idx >> 1) & 1); w_fullA += clock64() - tw; }
+        const int stA = ga & 1;
+        { const long long tw = clock64(); mbar_wait(fullA(stA), (ga >> 1) & 1); w_fullA += clock64() - tw; }
         const uint32_t a_hi_lo = a_lbo_f | (smem_u32(sA + stA * a_stage) >> 4);
         const uint32_t a_lo_lo = a_lbo_f | (smem_u32(sA + stA * a_stage + a_plane) >> 4);
         for (int t = 0; t < S.ntaps; ++t, ++bi) {
@@ -676,7 +741,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const uint32_t toff16 = (uint32_t)(p.window ? S.tapoff[t] : 0);          // rows are 16 B: row offset == 16-byte units
 #pragma unroll
             for (int sub = 0; sub < MSUB; ++sub) {
-              const uint32_t d = tmem_base + (uint32_t)(sub * NT);
+              const uint32_t d = tmem_acc + (uint32_t)(sub * NT);
               uint32_t acc_s = acc;
 #pragma unroll
               for (int kk = 0; kk < KB / 16; ++kk) {
@@ -701,8 +766,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         __syncwarp();
         if (++kb_m >= S.C / KB) { kb_m = 0; ++s_m; }
       }
+      if (leader) umma_commit(accFull(ab));
+      __syncwarp();
+      }
       if (leader) {
-        umma_commit(accFull);
         if (p.prof != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) {
           p.prof[6] = clock64() - t_m0;  // MMA issue loop total
           p.prof[7] = w_fullA;           // ... waiting for A
@@ -711,12 +778,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
       __syncwarp();
     }
+    }
+  } else if (PERSIST) {
+    // =================================== epilogue warps (persistent variant) ===================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
+    int it = 0;
+    for (int tile = tile_first; tile < tile_end; tile += tile_stride, ++it) {
+      set_tile(tile);
+      const bool last = tile + tile_stride >= tile_end;
+      run_epilogue(it, warp & 3, 0, last ? 3 : 1, true);
+    }
   }
 
   __syncthreads();
   if (warp == kProdWarps + 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    tmem_dealloc<TM_COLS>(tmem_base);
   }
 }
 
@@ -774,6 +851,12 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
 struct Variant { int msub, nt, kb; };
 
 static int g_small_nt64 = 1;
+static int g_persist = getenv("DDG_CONV_NO_PERSIST") ? 0 : 1;   // persistent variant (epilogue overlapped with the next tile's mainloop) when tiles > SMs
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148; }
+  return n;
+}
 static int g_nt256 = 1;  // N = 256 tiles for Cout % 256 == 0 (96 B/clk of operand reads per MMA instead of 128 B/clk at N = 128)
 
 // Output-channel tile.  N = 256 only when the grid still covers the machine (one wave of 128-row tiles at least).
@@ -787,12 +870,12 @@ static int pick_nt(int cout, long m_rows) {
 }
 static bool valid_nt(int nt) { return nt == 16 || nt == 64 || nt == 128 || nt == 256; }
 
-template <int MSUB, int NT, int KB, int PREC>
-static int launch_conv(const ConvDev& d, int n_tiles, cudaStream_t stream) {
+template <int MSUB, int NT, int KB, int PREC, bool PERSIST = false>
+static int launch_conv(ConvDev& d, int n_tiles, cudaStream_t stream) {
   using Cfg = ConvCfg<MSUB, NT, KB, PREC>;
   const size_t smem = 256 + (size_t)Cfg::NSB * Cfg::B_STAGE + 2 * (size_t)Cfg::NPL * Cfg::KCH * d.win_pitch;
   if (smem > 227 * 1024) { ddg_set_last_error("conv_tc: shared memory budget exceeded"); return DDG_ERR_UNSUPPORTED; }
-  auto kern = conv_tc_kernel<MSUB, NT, KB, PREC>;
+  auto kern = conv_tc_kernel<MSUB, NT, KB, PREC, PERSIST>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -801,7 +884,15 @@ static int launch_conv(const ConvDev& d, int n_tiles, cudaStream_t stream) {
   dim3 grid((d.Mtotal + Cfg::MT - 1) / Cfg::MT, n_tiles);
   if (d.tile2d) grid = dim3(d.N * d.tiles_x * d.tiles_y, n_tiles);
   if (d.batch_rows > 0) grid = dim3((d.batch_rows + Cfg::MT - 1) / Cfg::MT, n_tiles, d.Mtotal / d.batch_rows);
-  kern<<<grid, kThreads, smem, stream>>>(d);
+  d.tiles_m = (int)grid.x;
+  d.n_tiles = n_tiles;
+  if (PERSIST) {
+    const long total = (long)grid.x * n_tiles;
+    grid = dim3((unsigned)(total < num_sms() ? total : num_sms()));
+    kern<<<grid, kThreadsPersist, smem, stream>>>(d);
+  } else {
+    kern<<<grid, kThreads, smem, stream>>>(d);
+  }
   DDG_CHECK_LAUNCH();
   return DDG_OK;
 }
@@ -811,7 +902,12 @@ static int launch_conv(const ConvDev& d, int n_tiles, cudaStream_t stream) {
 using namespace ddg;
 
 extern "C" int ddg_conv_tile_n(int cout, long m_rows) { return pick_nt(cout, m_rows); }
-extern "C" int ddg_conv_set_nt256(int on) { const int old = g_nt256; g_nt256 = on & 1; g_small_nt64 = (on >> 1) & 1 ? 0 : 1; return old; }
+// tuning switches (bring-up / A-B measurements): bit 0 = N=256 tiles, bit 1 = no N=64 on tiny levels, bit 2 = no persistent variant
+extern "C" int ddg_conv_set_nt256(int on) {
+  const int old = g_nt256;
+  g_nt256 = on & 1; g_small_nt64 = (on >> 1) & 1 ? 0 : 1; g_persist = (on >> 2) & 1 ? 0 : 1;
+  return old;
+}
 
 extern "C" long ddg_conv_packed_bytes(int cout, int total_stages, int kb, int precision, int nt) {
   if (!valid_nt(nt)) return -1;
@@ -917,6 +1013,18 @@ extern "C" int ddg_conv2d_fwd(const ddg_conv_desc* c, cudaStream_t stream) {
     if (d.batch_rows > 0 && d.batch_rows % 256 != 0) msub = 1;
   }
   if (tile2d && d.Hout % (16 * msub) != 0) msub = 1;
+  // Persistent variant: more tiles than SMs, so every CTA runs >= 2 tiles back to back and the epilogue of tile i overlaps
+  // the mainloop of tile i+1 (two accumulator sets in TMEM: msub * nt <= 256 columns each).
+  bool persist = false;
+  if (g_persist && c->batch_rows == 0 && c->debug_prof == nullptr) {
+    auto tiles_for = [&](int ms) -> long {
+      return (tile2d ? (long)d.N * (d.Hout / (16 * ms)) * (d.Wout / 8) : ((long)d.Mtotal + 128 * ms - 1) / (128 * ms)) * n_tiles;
+    };
+    int ms = msub;
+    if (ms * nt > 256) ms = 1;
+    const bool have = (ms == 2 && (nt == 128 || nt == 64 || nt == 16)) || (ms == 1 && (nt == 256 || nt == 128));
+    if (have && tiles_for(ms) > num_sms()) { persist = true; msub = ms; }
+  }
   const int MT = 128 * msub;
   d.tile2d = tile2d ? 1 : 0;
   d.a_sbo = 128;
@@ -937,6 +1045,21 @@ extern "C" int ddg_conv2d_fwd(const ddg_conv_desc* c, cudaStream_t stream) {
   d.win_pitch = rows * 16;
   const int prec = c->precision == 1 ? 1 : 3;
 
+#define DDG_LAUNCH_P(MS, NTV, PR) return launch_conv<MS, NTV, 32, PR, true>(d, n_tiles, stream)
+  if (persist) {
+    if (prec == 3) {
+      if (nt == 256) DDG_LAUNCH_P(1, 256, 3);
+      if (nt == 128) { if (msub == 2) DDG_LAUNCH_P(2, 128, 3); else DDG_LAUNCH_P(1, 128, 3); }
+      if (nt == 64) DDG_LAUNCH_P(2, 64, 3);
+      if (nt == 16) DDG_LAUNCH_P(2, 16, 3);
+    } else {
+      if (nt == 256) DDG_LAUNCH_P(1, 256, 1);
+      if (nt == 128) { if (msub == 2) DDG_LAUNCH_P(2, 128, 1); else DDG_LAUNCH_P(1, 128, 1); }
+      if (nt == 64) DDG_LAUNCH_P(2, 64, 1);
+      if (nt == 16) DDG_LAUNCH_P(2, 16, 1);
+    }
+  }
+#undef DDG_LAUNCH_P
 #define DDG_LAUNCH(MS, NTV, PR) return launch_conv<MS, NTV, 32, PR>(d, n_tiles, stream)
   if (prec == 3) {
     if (nt == 256) { if (msub == 2) DDG_LAUNCH(2, 256, 3); else DDG_LAUNCH(1, 256, 3); }
