@@ -729,15 +729,15 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
         const SrcDev& S = p.src[s_m];
         const int stA = ga & 1;
         { const long long tw = clock64(); mbar_wait(fullA(stA), (ga >> 1) & 1); w_fullA += clock64() - tw; }
-        const uint32_t a_hi_lo = a_lbo_f | (smem_u32(sA + stA * a_stage) >> 4);
-        const uint32_t a_lo_lo = a_lbo_f | (smem_u32(sA + stA * a_stage + a_plane) >> 4);
+        const uint32_t a_hi_lo = a_lbo_f | ((smem_u32(sA + stA * a_stage) >> 4) & 0x3FFFu);
+        const uint32_t a_lo_lo = a_lbo_f | ((smem_u32(sA + stA * a_stage + a_plane) >> 4) & 0x3FFFu);
         for (int t = 0; t < S.ntaps; ++t, ++bi) {
           const int stB = bi % NSB;
           { const long long tw = clock64(); mbar_wait(fullB(stB), (bi / NSB) & 1); w_fullB += clock64() - tw; }
           tc_fence_after();
           if (leader) {
-            const uint32_t b_hi_lo = b_lbo_f | (smem_u32(sB + stB * Cfg::B_STAGE) >> 4);
-            const uint32_t b_lo_lo = b_lbo_f | (smem_u32(sB + stB * Cfg::B_STAGE + Cfg::B_PLANE) >> 4);
+            const uint32_t b_hi_lo = b_lbo_f | ((smem_u32(sB + stB * Cfg::B_STAGE) >> 4) & 0x3FFFu);
+            const uint32_t b_lo_lo = b_lbo_f | ((smem_u32(sB + stB * Cfg::B_STAGE + Cfg::B_PLANE) >> 4) & 0x3FFFu);
             const uint32_t toff16 = (uint32_t)(p.window ? S.tapoff[t] : 0);          // rows are 16 B: row offset == 16-byte units
 #pragma unroll
             for (int sub = 0; sub < MSUB; ++sub) {

@@ -13,6 +13,7 @@
 // and a slice of the pixel space (split-K); it streams pixel tiles of 128 rows through a 2-stage smem ring (producer warps
 // convert fp32 -> bf16 hi/lo; BF16x3 as in the forward), accumulates in TMEM across all its tiles, and finally adds its
 // block into dW with fp32 reductions (red.global.add).
+#include <cstdlib>
 #include "common.cuh"
 #include "ddgan_b200.h"
 
@@ -87,6 +88,9 @@ struct WgradDev {
   int tiles_per_cta;   // pixel tiles per split
   int n_tiles;         // total pixel tiles
   int xpitch_b;        // X window chunk pitch in bytes
+  int splits_pad;      // split slots per (co, ci, tap-group) block, a multiple of the cluster size; blockIdx.z = grp * splits_pad + split
+  int cs;              // cluster size along z: the CTAs of one cluster hold partial sums of the same dW block
+  int order;           // dW walk of the final reduction: 0 = taps fastest, then ci, then co (conv layouts); 1 = co fastest (NIN [in][out])
 };
 
 // NCI: input channels per CTA (GEMM N per tap); KT: pixel rows per stage (GEMM K per stage); NST: smem stages.
@@ -113,8 +117,8 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int co0 = blockIdx.x * MCO;
   const int ci0 = blockIdx.y * NCI;
-  const int grp = blockIdx.z % p.ngroups;
-  const int split = blockIdx.z / p.ngroups;
+  const int grp = blockIdx.z / p.splits_pad;
+  const int split = blockIdx.z - grp * p.splits_pad;
   const int t0 = grp * p.taps_per_group;
   const int t1 = min(t0 + p.taps_per_group, p.ntaps);
   int minoff = p.tapoff[t0], maxoff = p.tapoff[t0];
@@ -207,24 +211,35 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const __grid_con
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       w_mbar_arrive(full(st));
     }
-    // ============================ epilogue: TMEM -> dW (fp32 reductions) ============================
+    // ============================ epilogue 1/2: TMEM -> shared-memory staging in dW walk order ============================
+    // (the operand ring is dead once accFull fires).  Row pitches are chosen so that the 32 lanes (= 32 output channels) of one
+    // store hit 32 banks; split slots past the last pixel tile stage zeros.
     w_mbar_wait(accFull, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int quad = warp & 3, half = warp >> 2;
-    const int co = co0 + quad * 32 + lane;
-    constexpr int NCH = NCI / 32;
-    const int njobs = (t1 - t0) * NCH;
-    for (int job = half; job < njobs; job += 2) {
-      const int tl = job / NCH, ch = job % NCH;
-      float v[32];
-      w_tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tl * NCI + ch * 32), v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (co < p.Cout && my_tiles > 0) {
-        float* dst = p.dw + (size_t)co * p.s_co + (size_t)(t0 + tl) * p.s_tap;
+    {
+      float* S = reinterpret_cast<float*>(sbase);
+      const int quad = warp & 3, half = warp >> 2;
+      const int col = quad * 32 + lane;                // output channel inside the block
+      constexpr int NCH = NCI / 32;
+      const int ntl = t1 - t0;
+      const int njobs = ntl * NCH;
+      const int pa0 = NCI * ntl + 4;                   // order 0: S[co][tl][ci], 16-byte aligned rows, pitch = 4 (mod 32) words
+      for (int job = half; job < njobs; job += 2) {
+        const int tl = job / NCH, ch = job % NCH;
+        float v[32];
+        w_tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tl * NCI + ch * 32), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (my_tiles <= 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int ci = ci0 + ch * 32 + j;
-          if (ci < p.Cin_real) atomicAdd(dst + (size_t)ci * p.s_ci, v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        if (p.order == 0) {
+          float4* dst = reinterpret_cast<float4*>(S + col * pa0 + tl * NCI + ch * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) S[(tl * NCI + ch * 32 + j) * (MCO + 4) + col] = v[j];
         }
       }
     }
@@ -246,10 +261,10 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const __grid_con
         w_mbar_wait(full(st), (it / NST) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (leader) {
-          const uint32_t dy_hi = lbo_f | (w_smem_u32(sbase + st * stage_bytes) >> 4);
-          const uint32_t dy_lo = lbo_f | (w_smem_u32(sbase + st * stage_bytes + DY_PLANE) >> 4);
-          const uint32_t x_hi = lbo_f | (w_smem_u32(sbase + st * stage_bytes + NPL * DY_PLANE) >> 4);
-          const uint32_t x_lo = lbo_f | (w_smem_u32(sbase + st * stage_bytes + NPL * DY_PLANE + x_plane) >> 4);
+          const uint32_t dy_hi = lbo_f | ((w_smem_u32(sbase + st * stage_bytes) >> 4) & 0x3FFFu);   // CTA-local offset: in a cluster the window base is rank << 24
+          const uint32_t dy_lo = lbo_f | ((w_smem_u32(sbase + st * stage_bytes + DY_PLANE) >> 4) & 0x3FFFu);   // CTA-local offset: in a cluster the window base is rank << 24
+          const uint32_t x_hi = lbo_f | ((w_smem_u32(sbase + st * stage_bytes + NPL * DY_PLANE) >> 4) & 0x3FFFu);   // CTA-local offset: in a cluster the window base is rank << 24
+          const uint32_t x_lo = lbo_f | ((w_smem_u32(sbase + st * stage_bytes + NPL * DY_PLANE + x_plane) >> 4) & 0x3FFFu);   // CTA-local offset: in a cluster the window base is rank << 24
           for (int t = t0; t < t1; ++t) {
             const uint32_t xo = (uint32_t)(p.tapoff[t] - minoff);          // rows are 16 B: row offset == 16-byte units
             const uint32_t d = tmem_base + (uint32_t)((t - t0) * NCI);
@@ -286,6 +301,72 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const __grid_con
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
+  // ============================ epilogue 2/2: split-K reduction across the cluster, then one reduction into dW ============================
+  // Cluster rank r sums rows r, r + cs, ... of the staged block over all cs CTAs (distributed shared memory, contiguous reads) and
+  // issues red.global.add in dW order: cs x fewer L2 reductions than one scatter per CTA, and neighbouring lanes share sectors.
+  const int cs = p.cs;
+  uint32_t rank = 0;
+  if (cs > 1) {
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+  if (warp < kWProdWarps) {
+    const int ntl = t1 - t0;
+    const int rows = p.order == 0 ? MCO : ntl * NCI;
+    const int rlen = p.order == 0 ? NCI * ntl : MCO;          // multiple of 128 floats either way
+    const int pitch = rlen + 4;
+    const uint32_t s_local = w_smem_u32(sbase);
+    // per-warp scratch row behind the staging block: the summed row is re-read in dW order for sector-sharing reductions
+    float* T = reinterpret_cast<float*>(sbase) + (size_t)rows * pitch + (size_t)warp * rlen;
+    for (int a = (int)rank + cs * warp; a < rows; a += cs * kWProdWarps) {
+      uint32_t rbase[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        rbase[q] = s_local + (uint32_t)(a * pitch) * 4u;
+        if (cs > 1 && q < cs) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbase[q]) : "r"(rbase[q]), "r"((uint32_t)q));
+      }
+      for (int b4 = lane; b4 < rlen / 4; b4 += 32) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cs > 1) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (q < cs) {
+              float4 v;
+              asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(rbase[q] + (uint32_t)b4 * 16u) : "memory");
+              acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+          }
+        } else {
+          acc = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sbase) + (size_t)a * pitch)[b4];
+        }
+        reinterpret_cast<float4*>(T)[b4] = acc;
+      }
+      __syncwarp();
+      if (p.order == 0) {
+        const int co = co0 + a;
+        if (co < p.Cout) {
+          float* dst = p.dw + (size_t)co * p.s_co;
+          for (int f = lane; f < rlen; f += 32) {              // f walks (ci, tap) with the tap fastest, as dW does
+            const int ci_l = f / ntl, tl = f - ci_l * ntl;
+            const int ci = ci0 + ci_l;
+            if (ci < p.Cin_real) atomicAdd(dst + (size_t)ci * p.s_ci + (size_t)(t0 + tl) * p.s_tap, T[tl * NCI + ci_l]);
+          }
+        }
+      } else {
+        const int tl = a / NCI, ci = ci0 + (a - tl * NCI);
+        if (ci < p.Cin_real) {
+          float* dst = p.dw + (size_t)ci * p.s_ci + (size_t)(t0 + tl) * p.s_tap;
+          for (int b = lane; b < rlen; b += 32) {
+            const int co = co0 + b;
+            if (co < p.Cout) atomicAdd(dst + (size_t)co * p.s_co, T[b]);
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  // peers may still be reading this CTA's staging buffer
+  if (cs > 1) asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 template <int PREC, int NCI, int KT, int NST>
@@ -304,19 +385,62 @@ static int launch_wgrad(WgradDev& d, int Cout, int Cin_pad, int group_taps, cuda
   d.n_tiles = (d.Mtotal + KT - 1) / KT;
   constexpr int NPL = PREC == 3 ? 2 : 1;
   const size_t stage = (size_t)NPL * ((MCO / 8) * (KT + 1) * 16 + (NCI / 8) * d.xpitch_b);
-  const size_t smem = 128 + NST * stage;
+  size_t smem = 128 + NST * stage;
+  {
+    // the staging buffer of the final reduction reuses the operand ring
+    // rows x (row + 4) floats in either walk order, + one scratch row per reducing warp
+    const size_t r0 = (size_t)MCO * ((size_t)NCI * group_taps + 4), r1 = (size_t)NCI * group_taps * (MCO + 4);
+    const size_t staging = ((r0 > r1 ? r0 : r1) + (size_t)kWProdWarps * (NCI * group_taps > MCO ? NCI * group_taps : MCO)) * 4;
+    if (128 + staging > smem) smem = 128 + staging;
+  }
   if (smem > 227 * 1024) { ddg_set_last_error("conv2d_wgrad: shared memory budget exceeded (image too wide)"); return DDG_ERR_UNSUPPORTED; }
   const int gx = (Cout + MCO - 1) / MCO, gy = Cin_pad / NCI;
   const int base = gx * gy * d.ngroups;
-  int splits = (2 * 148 + base - 1) / base;        // ~2 waves of 148 SMs
-  if (splits > d.n_tiles) splits = d.n_tiles;
-  if (splits < 1) splits = 1;
+  // Split-K factor from a small cost model (cycles).  A cluster of cs CTAs reduces its partial blocks through distributed shared
+  // memory and issues one set of 128 x NCI x taps reductions into dW (the L2 retires ~100 scattered fp32 reductions per clock
+  // chip-wide; walked in dW order they share sectors, ~3x cheaper), so more splits shorten the serial MMA chain at little cost.
+  int splits = 1, cs = 1;
+  {
+    const double mma_cyc = (NCI >= 128 ? 64.0 : 36.0) * group_taps * (KT / 16) * (PREC == 3 ? 3 : 1);
+    const double chunks = (double)(KT * (MCO / 8) + (KT + span) * (NCI / 8)) / (kWProdWarps * 32);
+    const double prod_cyc = chunks * 35.0 * 2.0;     // ~35 instructions per 16-byte chunk, 2 producer warps per scheduler
+    const double t_tile = mma_cyc > prod_cyc ? mma_cyc : prod_cyc;
+    const double block_elems = 128.0 * NCI * group_taps;
+    const double t_fixed = 8000.0 + block_elems / 32.0;   // setup + TMEM -> smem staging
+    double best = 1e30;
+    const int smax = d.n_tiles < 4 * 148 ? d.n_tiles : 4 * 148;
+    // measured on B200: CTA pairs (one TPC) always co-schedule; clusters of 4 / 8 full-SM CTAs wait for whole-GPC slots and lose 1.5-2x
+    static int cs_max = getenv("DDG_WGRAD_CS_MAX") ? atoi(getenv("DDG_WGRAD_CS_MAX")) : 2;
+    for (int c2 = 1; c2 <= cs_max; c2 *= 2) {
+      for (int sp = c2; sp <= smax || sp == c2; sp += c2) {
+        if (sp > d.n_tiles && sp > c2) break;
+        const int tpc = (d.n_tiles + sp - 1) / sp;
+        const double ctas = (double)base * sp;
+        const double waves = (double)(((long)ctas + 147) / 148);
+        const double t_red = c2 > 1 ? 3000.0 + block_elems / 64.0 : 0.0;   // cluster barriers + DSMEM sweep of this CTA's rows
+        const double t = waves * (tpc * t_tile + t_fixed + t_red) + (ctas / c2) * block_elems / 300.0;
+        if (t < best) { best = t; splits = sp; cs = c2; }
+      }
+    }
+  }
   d.tiles_per_cta = (d.n_tiles + splits - 1) / splits;
-  splits = (d.n_tiles + d.tiles_per_cta - 1) / d.tiles_per_cta;
+  d.splits_pad = splits;
+  d.cs = cs;
+  d.order = (d.s_co < d.s_ci) ? 1 : 0;
   auto kern = wgrad_tc_kernel<PREC, NCI, KT, NST>;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
-  kern<<<dim3(gx, gy, d.ngroups * splits), kWThreads, smem, stream>>>(d);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(gx, gy, d.ngroups * splits);
+  cfg.blockDim = dim3(kWThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = cs;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, d);
+  if (e != cudaSuccess) { ddg_set_last_error(cudaGetErrorString(e)); return DDG_ERR_LAUNCH; }
   DDG_CHECK_LAUNCH();
   return DDG_OK;
 }
