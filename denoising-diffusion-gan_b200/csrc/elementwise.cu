@@ -412,6 +412,34 @@ extern "C" int ddg_gn_prepare(const double* stats_a, int Ca, const double* stats
   return DDG_OK;
 }
 
+namespace ddg {
+__global__ void zero_border_kernel(float* __restrict__ buf, int N, int H, int W, int C4) {
+  const int bp = 2 * (W + 2) + 2 * H;                // frame pixels per image
+  const long total = (long)N * bp * C4;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    long r = i / C4;
+    const int b = (int)(r % bp);
+    const int n = (int)(r / bp);
+    int hp, wp;
+    if (b < W + 2) { hp = 0; wp = b; }
+    else if (b < 2 * (W + 2)) { hp = H + 1; wp = b - (W + 2); }
+    else { const int k = b - 2 * (W + 2); hp = 1 + (k >> 1); wp = (k & 1) ? W + 1 : 0; }
+    reinterpret_cast<float4*>(buf + ((size_t)(n * (H + 2) + hp) * (W + 2) + wp) * (size_t)(C4 * 4))[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+}  // namespace ddg
+
+extern "C" int ddg_zero_border(float* buf, int N, int H, int W, int C, cudaStream_t stream) {
+  if (!buf || N <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 4 != 0) { ddg_set_last_error("zero_border: bad args"); return DDG_ERR_ARG; }
+  const long total = (long)N * (2 * (W + 2) + 2 * H) * (C / 4);
+  long blocks = (total + 255) / 256;
+  if (blocks > 148L * 8) blocks = 148L * 8;
+  ddg::zero_border_kernel<<<(int)blocks, 256, 0, stream>>>(buf, N, H, W, C / 4);
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}
+
 extern "C" int ddg_spatial_sum(const float* x, float* out, int N, int H, int W, int C, int act, cudaStream_t stream) {
   if (!x || !out) { ddg_set_last_error("spatial_sum: bad args"); return DDG_ERR_ARG; }
   dim3 grid((C + 127) / 128, N);

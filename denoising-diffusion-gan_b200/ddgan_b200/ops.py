@@ -8,6 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import math
 
+import os
 import torch
 
 from . import _lib
@@ -149,9 +150,24 @@ def sample_posterior(x0, x_t, noise, t, coef1, coef2, logvar, out=None):
 # ---------------------------------------------------------------------------------------------------------
 # internal layout (PNHWC) helpers
 # ---------------------------------------------------------------------------------------------------------
-def alloc_pnhwc(n, h, w, c, device) -> torch.Tensor:
-    """Zero-initialised [N, H+2, W+2, C]; kernels only ever write the interior so the border stays zero."""
-    return torch.zeros(n, h + 2, w + 2, c, device=device, dtype=torch.float32)
+_POISON = bool(os.environ.get('DDG_POISON_ALLOC'))   # test aid: NaN-fill fresh interiors to catch kernels that skip elements
+
+
+def alloc_pnhwc(n, h, w, c, device, full=True) -> torch.Tensor:
+    """[N, H+2, W+2, C] with a zero border.  full=False: only the frame is cleared (for producers that write every interior
+    element and channel); full=True zero-fills the whole buffer."""
+    if full or c % 4 != 0:
+        return torch.zeros(n, h + 2, w + 2, c, device=device, dtype=torch.float32)
+    out = torch.empty(n, h + 2, w + 2, c, device=device, dtype=torch.float32)
+    if _POISON:
+        out.fill_(float('nan'))
+    check(lib().ddg_zero_border(ptr(out), n, h, w, c, stream()), 'zero_border')
+    return out
+
+
+def empty_like_pnhwc(x) -> torch.Tensor:
+    n, hp, wp, c = x.shape
+    return alloc_pnhwc(n, hp - 2, wp - 2, c, x.device, full=False)
 
 
 def to_pnhwc(a, b=None, cpad=None, out=None, scale=1.0, shift=0.0):
@@ -165,7 +181,7 @@ def to_pnhwc(a, b=None, cpad=None, out=None, scale=1.0, shift=0.0):
     if cpad is None:
         cpad = pad_c(ca + cb)
     if out is None:
-        out = alloc_pnhwc(n, h, w, cpad, a.device)
+        out = alloc_pnhwc(n, h, w, cpad, a.device, full=False)
     check(lib().ddg_nchw_to_pnhwc(ptr(a), ca, ptr(b), cb, ptr(out), n, h, w, cpad, scale, shift, stream()), 'nchw_to_pnhwc')
     return out
 
@@ -205,14 +221,14 @@ def fir_pnhwc(x, mode, out, scale=None, shift=None, act=ACT_NONE, gain=1.0):
 def affine_act_fwd(x, scale, shift, act, out=None):
     n, hp, wp, c = x.shape
     if out is None:
-        out = torch.zeros_like(x)
+        out = empty_like_pnhwc(x)
     check(lib().ddg_affine_act_fwd(ptr(x), ptr(scale), ptr(shift), ptr(out), n, hp - 2, wp - 2, c, act, stream()), 'affine_act_fwd')
     return out
 
 
 def affine_act_bwd(x, dy, scale, shift, act, need_sums=True):
     n, hp, wp, c = x.shape
-    dx = torch.zeros_like(x)
+    dx = empty_like_pnhwc(x)
     sums = torch.zeros(n, c, 2, dtype=torch.float64, device=x.device) if need_sums else None
     check(lib().ddg_affine_act_bwd(ptr(x), ptr(dy), ptr(scale), ptr(shift), ptr(dx), ptr(sums), n, hp - 2, wp - 2, c, act, stream()),
           'affine_act_bwd')
@@ -228,13 +244,13 @@ def stats_fwd(x):
 
 def stats_bwd(x, g):
     n, hp, wp, c = x.shape
-    dx = torch.zeros_like(x)
+    dx = empty_like_pnhwc(x)
     check(lib().ddg_stats_bwd(ptr(x), ptr(g), ptr(dx), n, hp - 2, wp - 2, c, stream()), 'stats_bwd')
     return dx
 
 
 def conv_wgrad(x, dy, dw, n, hp, wp, cout, cin_real, cin_pad, taps, s_co, s_ci, s_tap, precision=3, xpitch=None, dypitch=None,
-               dy_cpad=None, x_elem_offset=0):
+               dy_cpad=None, x_elem_offset=0, flops=None):
     """dw[co*s_co + ci*s_ci + t*s_tap] += sum_q dy[q][co] * x[q + tap_t][ci]  (dw zero-initialised by the caller)."""
     d = _lib.WgradDesc()
     d.x = x.data_ptr() + 4 * x_elem_offset; d.dy = ptr(dy); d.dw = ptr(dw)
@@ -251,10 +267,33 @@ def conv_wgrad(x, dy, dw, n, hp, wp, cout, cin_real, cin_pad, taps, s_co, s_ci, 
         a.record()
         check(lib().ddg_conv2d_wgrad(C.byref(d), stream()), 'conv2d_wgrad')
         b.record()
-        PROFILE['records'].append(('wgrad_tc', 2.0 * n * (hp - 2) * (wp - 2) * cout * cin_pad * len(taps), a, b))
+        PROFILE['records'].append(('wgrad_tc', flops if flops is not None else 2.0 * n * (hp - 2) * (wp - 2) * cout * cin_pad * len(taps), a, b))
         return dw
     check(lib().ddg_conv2d_wgrad(C.byref(d), stream()), 'conv2d_wgrad')
     return dw
+
+
+def gemm_rows(x, W, b=None, precision=3):
+    """y[N, J] = x[N, K] @ W[J, K]^T + b on the tensor-core conv kernel (a 1x1 conv over N 'pixels'); K % 32 == 0."""
+    n, k = x.shape
+    j = W.shape[0]
+    cw = ConvWeights(j, [(k, 1)], x.device, precision=precision, m_rows=n)
+    cw.pack_segment(0, W, k, k, 1, 0)
+    out = torch.empty(n, j, device=x.device, dtype=torch.float32)
+    d = build_conv_desc(cw, [conv_src(x, k, TAPS_1X1, padded=False)], n, 1, 1, out, out_mode=OUT_NHWC, bias=b)
+    conv_launch(d)
+    return out
+
+
+def gemm_tn(a, b, precision=3):
+    """out[Ca, Cb] = a[Q, Ca]^T @ b[Q, Cb] (contraction over rows) on the tensor-core weight-gradient kernel.
+    Ca % 8 == 0, Cb % 32 == 0."""
+    q, ca = a.shape
+    cb = b.shape[1]
+    out = torch.zeros(ca, cb, device=a.device, dtype=torch.float32)
+    conv_wgrad(b, a, out, 1, q, 1, ca, cb, cb, [(0, 0)], cb, 1, 0, precision=precision, xpitch=cb, dypitch=ca, dy_cpad=ca,
+               flops=2.0 * q * ca * cb)
+    return out
 
 
 def minibatch_stddev(x, out, group):

@@ -71,7 +71,7 @@ def _conv_forward(x, w, bias, addvec, sp):
         out = torch.zeros(sp.n, sp.cout, sp.hout, sp.wout, device=x.device)
         mode, out_c = ops.OUT_NCHW, 0
     else:
-        out = ops.alloc_pnhwc(sp.n, sp.hout, sp.wout, sp.cpad_out, x.device)
+        out = ops.alloc_pnhwc(sp.n, sp.hout, sp.wout, sp.cpad_out, x.device, full=(sp.cout != sp.cpad_out))
         mode, out_c = ops.OUT_PNHWC, sp.cpad_out
     ops.conv2d_fused(cw, [ops.conv_src(x, sp.cpad_in, sp.taps)], sp.n, sp.hout, sp.wout, out, out_mode=mode, out_c=out_c,
                      hp=sp.hp, wp=sp.wp, bias=bias, addvec=addvec, addvec_stride=(addvec.shape[1] if addvec is not None else 0))
@@ -110,8 +110,19 @@ class ConvFn(Function):
         dyc = dy.contiguous()
         dx = DgradFn.apply(dyc, w, sp) if ctx.needs_input_grad[0] else None
         dw = WgradFn.apply(x, dyc, sp) if ctx.needs_input_grad[1] else None
-        db = dyc.sum(dim=(0, 1, 2))[:sp.cout] if (ctx.has_bias and ctx.needs_input_grad[2]) else None
-        dav = dyc.sum(dim=(1, 2))[:, :sp.cout] if (ctx.has_addvec and ctx.needs_input_grad[3]) else None
+        need_db = ctx.has_bias and ctx.needs_input_grad[2]
+        need_dav = ctx.has_addvec and ctx.needs_input_grad[3]
+        db = dav = None
+        if need_db or need_dav:
+            if torch.is_grad_enabled() and dyc.requires_grad:
+                # create_graph pass: keep the reductions differentiable
+                db = dyc.sum(dim=(0, 1, 2))[:sp.cout] if need_db else None
+                dav = dyc.sum(dim=(1, 2))[:, :sp.cout] if need_dav else None
+            else:
+                # one streaming pass of the PNHWC reduction kernel gives the per-(sample, channel) sums both gradients need
+                nc = ops.stats_fwd(dyc)[:, :sp.cout, 0]
+                dav = nc.float() if need_dav else None
+                db = nc.sum(0).float() if need_db else None
         return dx, dw, db, dav, None
 
 
@@ -130,7 +141,7 @@ class DgradFn(Function):
         m_rows = sp.n * sp.hp * sp.wp if len(sp.taps) > 1 else sp.n * (sp.hp - 2) * (sp.wp - 2)
         cw = ops.ConvWeights(sp.cpad_in, [(cy, len(sp.taps))], dy.device, precision=sp.prec, m_rows=m_rows)
         cw.pack_segment(0, w, sp.cout, sp.s_ci, sp.s_co, sp.s_tap)   # roles of co / ci swapped
-        dx = ops.alloc_pnhwc(sp.n, sp.hp - 2, sp.wp - 2, sp.cpad_in, dy.device)
+        dx = ops.alloc_pnhwc(sp.n, sp.hp - 2, sp.wp - 2, sp.cpad_in, dy.device, full=False)
         taps = [(-dr, -ds) for dr, ds in sp.taps]
         ops.conv2d_fused(cw, [ops.conv_src(dye, cy, taps)], sp.n, sp.hp - 2, sp.wp - 2, dx)
         if sp.cin < sp.cpad_in:
@@ -220,9 +231,9 @@ class FirFn(Function):
         x = x.contiguous()
         n, hp, wp, c = x.shape
         if mode == 1:
-            out = ops.alloc_pnhwc(n, 2 * (hp - 2), 2 * (wp - 2), c, x.device)
+            out = ops.alloc_pnhwc(n, 2 * (hp - 2), 2 * (wp - 2), c, x.device, full=False)
         elif mode == 2:
-            out = ops.alloc_pnhwc(n, (hp - 2) // 2, (wp - 2) // 2, c, x.device)
+            out = ops.alloc_pnhwc(n, (hp - 2) // 2, (wp - 2) // 2, c, x.device, full=False)
         elif mode == 3:
             out = torch.zeros(n, (hp - 2) // 2 + 3, (wp - 2) // 2 + 3, 4 * c, device=x.device)
         else:
@@ -296,22 +307,35 @@ def group_norm_act(x, h, w, groups, gamma, beta, act, eps=1e-6):
     return AffineActFn.apply(x, scale, shift, act)
 
 
+def _tc_linear(n, k, j):
+    """Large projections (the batched AdaGN style / Dense_0 GEMMs) go to the tcgen05 kernels; small ones stay on the SIMT kernel."""
+    return j >= 1024 and k % 32 == 0 and n % 8 == 0 and j % 32 == 0
+
+
 class LinearFn(Function):
-    """y = x W^T + b on [N, K] rows through ddg_linear (forward and both gradient GEMMs)."""
+    """y = x W^T + b on [N, K] rows (forward and both gradient GEMMs): ddg_linear, or the tensor-core GEMMs for wide layers."""
 
     @staticmethod
     def forward(ctx, x, W, b):
         x, W = x.contiguous(), W.contiguous()
         ctx.save_for_backward(x, W)
         ctx.has_b = b is not None
+        if _tc_linear(x.shape[0], x.shape[1], W.shape[0]):
+            return ops.gemm_rows(x, W, b)
         return ops.linear(x, W, b)
 
     @staticmethod
     def backward(ctx, dy):
         x, W = ctx.saved_tensors
         dy = dy.contiguous()
-        dx = ops.linear(dy, W.t().contiguous()) if ctx.needs_input_grad[0] else None
-        dW = ops.linear(dy.t().contiguous(), x.t().contiguous()) if ctx.needs_input_grad[1] else None
+        tc = _tc_linear(x.shape[0], x.shape[1], W.shape[0])
+        dx = dW = None
+        if ctx.needs_input_grad[0]:
+            # dx[n][k] = sum_j dy[n][j] W[j][k]: contraction over the J rows of dy^T and W
+            dx = ops.gemm_tn(dy.t().contiguous(), W) if tc else ops.linear(dy, W.t().contiguous())
+        if ctx.needs_input_grad[1]:
+            # dW[j][k] = sum_n dy[n][j] x[n][k]: contraction over the batch rows
+            dW = ops.gemm_tn(dy, x) if tc else ops.linear(dy.t().contiguous(), x.t().contiguous())
         db = dy.sum(0) if (ctx.has_b and ctx.needs_input_grad[2]) else None
         return dx, dW, db
 

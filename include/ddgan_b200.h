@@ -91,6 +91,9 @@ int ddg_fir_pnhwc(const float* x, const float* scale, const float* shift, int ac
 int ddg_minibatch_stddev(const float* x, float* out, int N, int H, int W, int C, int Cpad, int group, cudaStream_t stream);
 /* out[n][c] = sum_{h,w} act(x[n][h][w][c]) over the interior of a PNHWC tensor (discriminator.py:163-165) */
 int ddg_spatial_sum(const float* x, float* out, int N, int H, int W, int C, int act, cudaStream_t stream);
+/* zero the one-pixel frame of a PNHWC buffer [N][H+2][W+2][C] (C % 4 == 0): kernels write interiors only, so a fresh buffer needs
+ * just its border cleared to serve as the zero padding of the next 3x3 conv (ncsnpp convs use padding=1, layerspp.py:33) */
+int ddg_zero_border(float* buf, int N, int H, int W, int C, cudaStream_t stream);
 /* row softmax of the attention logits (layerspp.py:116-118): p[r][0:T] = softmax(s[r][0:T]), p[r][T:ldp] = 0 */
 int ddg_softmax_rows(const float* s, float* p, long rows, int T, int lds, int ldp, cudaStream_t stream);
 

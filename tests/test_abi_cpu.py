@@ -36,7 +36,8 @@ def test_host_side_helpers_without_gpu():
     assert lib.ddg_upfirdn2d_out_size(32, 1, 2, 1, 1, 4) == 16
     assert lib.ddg_upfirdn2d_out_size(16, 2, 1, 2, 1, 4) == 32
     assert lib.ddg_upfirdn2d_out_size(32, 1, 1, 2, 2, 4) == 33
-    assert lib.ddg_conv_tile_n(256, 1000) == 128 and lib.ddg_conv_tile_n(256, 64 * 34 * 34) == 256
+    # tiny levels take narrow tiles (more CTAs, shorter MMA chains); one wave of 128-row tiles switches to N = 256
+    assert lib.ddg_conv_tile_n(256, 1000) == 64 and lib.ddg_conv_tile_n(256, 6400) == 128 and lib.ddg_conv_tile_n(256, 64 * 34 * 34) == 256
     assert lib.ddg_conv_tile_n(3, 10 ** 6) == 16 and lib.ddg_conv_tile_n(64, 10 ** 6) == 64 and lib.ddg_conv_tile_n(128, 10 ** 6) == 128
     # 3x3 conv 256->256: 8 k-blocks x 9 taps, 2 n-tiles, hi+lo planes of 32x128 bf16
     assert lib.ddg_conv_packed_bytes(256, 72, 32, 3, 128) == 2 * 72 * 32 * 128 * 2 * 2

@@ -72,6 +72,19 @@ def test_groupnorm_fir_linear_grads():
     g = torch.autograd.grad((TG.LinearFn.apply(xd, Wd, bd) * gy.to(DEV)).sum(), (xd, Wd, bd))
     for a, b_ in zip(g, g_ref):
         assert O.rel_l2(a.cpu(), b_) < 1e-5
+    # wide linear (the batched AdaGN style projection shape): forward and both gradient GEMMs run on the tcgen05 kernels
+    xl = seeded((64, 256), 13); W = seeded((4096, 256), 14, 0.1); b = seeded((4096,), 15)
+    assert TG._tc_linear(64, 256, 4096)
+    xr, Wr, br = xl.clone().requires_grad_(True), W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    gy = seeded((64, 4096), 16)
+    y_ref = F.linear(xr, Wr, br)
+    g_ref = torch.autograd.grad((y_ref * gy).sum(), (xr, Wr, br))
+    xd, Wd, bd = xl.to(DEV).requires_grad_(True), W.to(DEV).requires_grad_(True), b.to(DEV).requires_grad_(True)
+    yd = TG.LinearFn.apply(xd, Wd, bd)
+    assert O.rel_l2(yd.detach().cpu(), y_ref.detach()) < 1e-5
+    g = torch.autograd.grad((yd * gy.to(DEV)).sum(), (xd, Wd, bd))
+    for a, b_ in zip(g, g_ref):
+        assert O.rel_l2(a.cpu(), b_) < 1e-5
 
 
 def _nets():
