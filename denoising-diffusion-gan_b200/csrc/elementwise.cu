@@ -413,6 +413,40 @@ extern "C" int ddg_gn_prepare(const double* stats_a, int Ca, const double* stats
 }
 
 namespace ddg {
+// one thread per (sample, group); see ddg_gn_prepare_bwd in the header for the contract
+__global__ void gn_prepare_bwd_kernel(const double* __restrict__ st, const float* __restrict__ gamma, int gb_stride, int per_sample,
+                                      const float* __restrict__ dscale, const float* __restrict__ dshift, double* __restrict__ dst,
+                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int N, int C, int HW, int G, float eps) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * G) return;
+  const int n = idx / G, g = idx - n * G;
+  const int cpg = C / G;
+  const size_t base = (size_t)n * C + (size_t)g * cpg;
+  double s1 = 0, s2 = 0;
+  for (int j = 0; j < cpg; ++j) { s1 += st[(base + j) * 2]; s2 += st[(base + j) * 2 + 1]; }
+  const double cnt = (double)cpg * HW;
+  const double mean = s1 / cnt;
+  double var = s2 / cnt - mean * mean;
+  const bool clamped = var < 0;
+  if (clamped) var = 0;
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  double d_rstd = 0, d_mean = 0;
+  for (int j = 0; j < cpg; ++j) {
+    const int c = g * cpg + j;
+    const double ga = gamma ? (double)(per_sample ? gamma[(size_t)n * gb_stride + c] : gamma[c]) : 1.0;
+    const double ds = dscale[base + j], dh = dshift[base + j];
+    const double t = ds - mean * dh;                 // scale = ga*rstd, shift = be - mean*ga*rstd
+    dgamma[base + j] = (float)(rstd * t);
+    dbeta[base + j] = (float)dh;
+    d_rstd += ga * t;
+    d_mean -= rstd * ga * dh;
+  }
+  const double d_var = clamped ? 0.0 : -0.5 * d_rstd * rstd * rstd * rstd;
+  const double d_s1 = d_mean / cnt - 2.0 * mean * d_var / cnt;
+  const double d_s2 = d_var / cnt;
+  for (int j = 0; j < cpg; ++j) { dst[(base + j) * 2] = d_s1; dst[(base + j) * 2 + 1] = d_s2; }
+}
+
 __global__ void zero_border_kernel(float* __restrict__ buf, int N, int H, int W, int C4) {
   const int bp = 2 * (W + 2) + 2 * H;                // frame pixels per image
   const long total = (long)N * bp * C4;
@@ -429,6 +463,17 @@ __global__ void zero_border_kernel(float* __restrict__ buf, int N, int H, int W,
   }
 }
 }  // namespace ddg
+
+extern "C" int ddg_gn_prepare_bwd(const double* stats, const float* gamma, int gb_stride, int per_sample, const float* dscale,
+                                  const float* dshift, double* dstats, float* dgamma, float* dbeta, int N, int C, int HW, int G,
+                                  float eps, cudaStream_t stream) {
+  if (!stats || !dscale || !dshift || !dstats || !dgamma || !dbeta || G <= 0 || C % G != 0) { ddg_set_last_error("gn_prepare_bwd: bad args"); return DDG_ERR_ARG; }
+  const int total = N * G;
+  ddg::gn_prepare_bwd_kernel<<<(total + 127) / 128, 128, 0, stream>>>(stats, gamma, gb_stride, per_sample, dscale, dshift, dstats, dgamma,
+                                                                    dbeta, N, C, HW, G, eps);
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}
 
 extern "C" int ddg_zero_border(float* buf, int N, int H, int W, int C, cudaStream_t stream) {
   if (!buf || N <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 4 != 0) { ddg_set_last_error("zero_border: bad args"); return DDG_ERR_ARG; }

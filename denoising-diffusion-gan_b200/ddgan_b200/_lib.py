@@ -54,6 +54,7 @@ _SIGNATURES = {
     'ddg_nchw_to_pnhwc': ([_P, _I, _P, _I, _P, _I, _I, _I, _I, _F, _F, _P], _I),
     'ddg_pnhwc_to_nchw': ([_P, _P] + [_I] * 6 + [_P], _I),
     'ddg_gn_prepare': ([_P, _I, _P, _I, _P, _P, _I, _I, _P, _P, _I, _I, _I, _F, _P], _I),
+    'ddg_gn_prepare_bwd': ([_P, _P, _I, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _P], _I),
     'ddg_fir_pnhwc': ([_P, _P, _P, _I, _P] + [_I] * 6 + [_F, _P], _I),
     'ddg_minibatch_stddev': ([_P, _P] + [_I] * 6 + [_P], _I),
     'ddg_spatial_sum': ([_P, _P] + [_I] * 5 + [_P], _I),

@@ -205,6 +205,15 @@ def gn_prepare(stats_a, ca, stats_b, cb, gamma, beta, gb_stride, per_sample, n, 
                                ptr(scale), ptr(shift), n, hw, groups, eps, stream()), 'gn_prepare')
 
 
+def gn_prepare_bwd(stats, gamma, gb_stride, per_sample, dscale, dshift, n, c, hw, groups, eps=1e-6):
+    dstats = torch.empty(n, c, 2, dtype=torch.float64, device=stats.device)
+    dgamma = torch.empty(n, c, dtype=torch.float32, device=stats.device)
+    dbeta = torch.empty(n, c, dtype=torch.float32, device=stats.device)
+    check(lib().ddg_gn_prepare_bwd(ptr(stats), ptr(gamma), gb_stride, int(per_sample), ptr(dscale), ptr(dshift), ptr(dstats),
+                                   ptr(dgamma), ptr(dbeta), n, c, hw, groups, eps, stream()), 'gn_prepare_bwd')
+    return dstats, dgamma, dbeta
+
+
 def fir_pnhwc(x, mode, out, scale=None, shift=None, act=ACT_NONE, gain=1.0):
     """mode 1 up2, 2 down2, 3 pad(2,2)+space-to-depth, 4 adjoint of 3 (x is the s2d tensor, out the image)."""
     if mode == 4:

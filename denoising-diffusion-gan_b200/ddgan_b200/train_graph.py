@@ -287,23 +287,43 @@ class AffineActFn(Function):
         return dx, sums[..., 0].to(torch.float32), sums[..., 1].to(torch.float32), None
 
 
+class GnCoefFn(Function):
+    """(scale, shift)[N, C] of a GroupNorm from the per-(sample, channel) sums: one kernel each way (ddg_gn_prepare / _bwd)
+    instead of ~45 small float64 torch kernels per normalisation.  First-order only: the generator's norms never sit under
+    the R1 double backward (the discriminator has none)."""
+
+    @staticmethod
+    def forward(ctx, st, gamma, beta, groups, hw, eps):
+        n, c = st.shape[0], st.shape[1]
+        per_sample = gamma.dim() == 2
+        assert gamma.stride(-1) == 1 and beta.stride(-1) == 1
+        gb_stride = gamma.stride(0) if per_sample else 0
+        if per_sample:
+            assert beta.stride(0) == gb_stride
+        st = st.contiguous()
+        scale = torch.empty(n, c, device=st.device, dtype=torch.float32)
+        shift = torch.empty(n, c, device=st.device, dtype=torch.float32)
+        ops.gn_prepare(st, c, None, 0, gamma, beta, gb_stride, per_sample, n, hw, groups, scale, shift, eps)
+        ctx.save_for_backward(st, gamma)
+        ctx.cfg = (groups, hw, eps, per_sample, gb_stride)
+        return scale, shift
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dscale, dshift):
+        st, gamma = ctx.saved_tensors
+        groups, hw, eps, per_sample, gb_stride = ctx.cfg
+        n, c = st.shape[0], st.shape[1]
+        dst, dga, dbe = ops.gn_prepare_bwd(st, gamma, gb_stride, per_sample, dscale.contiguous(), dshift.contiguous(), n, c, hw,
+                                           groups, eps)
+        if not per_sample:
+            dga, dbe = dga.sum(0), dbe.sum(0)
+        return dst, dga, dbe, None, None, None
+
+
 def group_norm_act(x, h, w, groups, gamma, beta, act, eps=1e-6):
     """gamma / beta: [N, C] (AdaGN) or [C] (affine GroupNorm).  Statistics in float64 as in the fused plan."""
-    n, c = x.shape[0], x.shape[-1]
-    cpg = c // groups
-    st = StatsFn.apply(x).view(n, groups, cpg, 2).sum(2)
-    cnt = float(cpg * h * w)
-    mean = st[..., 0] / cnt
-    var = (st[..., 1] / cnt - mean * mean).clamp_min(0.0)
-    rstd = torch.rsqrt(var + eps)
-    mean_c = mean.repeat_interleave(cpg, dim=1)
-    rstd_c = rstd.repeat_interleave(cpg, dim=1)
-    g64 = gamma.double() if gamma.dim() == 2 else gamma.double().unsqueeze(0)
-    b64 = beta.double() if beta.dim() == 2 else beta.double().unsqueeze(0)
-    scale = (g64 * rstd_c).to(torch.float32)
-    shift = (b64 - mean_c * g64 * rstd_c).to(torch.float32)
-    if scale.shape[0] != n:
-        scale, shift = scale.expand(n, c), shift.expand(n, c)
+    scale, shift = GnCoefFn.apply(StatsFn.apply(x), gamma, beta, groups, h * w, eps)
     return AffineActFn.apply(x, scale, shift, act)
 
 

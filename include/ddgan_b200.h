@@ -79,6 +79,11 @@ int ddg_pnhwc_to_nchw(const float* x, float* out, int N, int H, int W, int C, in
 int ddg_gn_prepare(const double* stats_a, int Ca, const double* stats_b, int Cb, const float* gamma, const float* beta,
                    int gb_stride, int per_sample, float* scale, float* shift, int N, int HW, int G, float eps,
                    cudaStream_t stream);
+/* backward of ddg_gn_prepare (training): given d(scale), d(shift) [N][C] returns d(stats) [N][C][2] (double), and the per-sample
+ * d(gamma), d(beta) [N][C] (sum over N on the caller's side for a shared affine).  Same group statistics as the forward. */
+int ddg_gn_prepare_bwd(const double* stats, const float* gamma, int gb_stride, int per_sample, const float* dscale,
+                       const float* dshift, double* dstats, float* dgamma, float* dbeta, int N, int C, int HW, int G, float eps,
+                       cudaStream_t stream);
 /* FIR resampling on PNHWC with the AdaGN+SiLU prologue fused on load (layerspp.py:279-293): [1,3,3,1] (x) [1,3,3,1]
  * mode 1: up x2 (upsample_2d, up_or_down_sampling.py:200-228), mode 2: down x2 (downsample_2d, :231-261),
  * mode 3: pad (2,2) FIR (H -> H+1) written space-to-depth for the stride-2 conv of conv_downsample_2d (:149-183):
