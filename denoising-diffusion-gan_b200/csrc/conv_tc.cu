@@ -863,7 +863,8 @@ static int g_nt256 = 1;  // N = 256 tiles for Cout % 256 == 0 (96 B/clk of opera
 static int pick_nt(int cout, long m_rows) {
   if (cout <= 16) return 16;
   if (cout <= 64) return 64;
-  if (g_nt256 && cout % 256 == 0 && ((m_rows + 127) / 128) * (cout / 256) >= 148) return 256;
+  // (>= 0.8 of a wave: below N = 256 every MMA re-reads a 4 KB A tile for 4 KB of B, right at the 128 B/clk shared-memory limit)
+  if (g_nt256 && cout % 256 == 0 && ((m_rows + 127) / 128) * (cout / 256) >= 120) return 256;
   // tiny spatial levels (4x4, 8x8): narrow tiles multiply the CTA count and shorten each CTA's serial MMA chain
   if (g_small_nt64 && cout % 64 == 0 && ((m_rows + 127) / 128) * (cout / 64) <= 148) return 64;
   return 128;

@@ -201,22 +201,22 @@ class GeneratorEngine(_EngineBase):
         self._step(lambda: self._stats_arena[:used_holder[0]].zero_())
         # z mapping (ncsnpp_generator_adagn.py:51-56, 271-277) and time embedding (:295-303)
         zb = [torch.empty(N, zd, device=dev) for _ in range(2)]
-        self._step(lambda: ops.linear(self.z_in, P['z_transform.1.weight'], P['z_transform.1.bias'], act_out=ops.ACT_SILU,
-                                      pixel_norm=True, out=zb[0]))
+        # activations are applied as the prologue of the consuming GEMM, so every layer after the first (K = nz is not a
+        # multiple of the K block) runs on the tensor-core GEMM path
+        self._step(lambda: ops.linear(self.z_in, P['z_transform.1.weight'], P['z_transform.1.bias'], pixel_norm=True, out=zb[0]))
         cur = 0
         for i in range(cfg.n_mlp):
             nme = f'z_transform.{3 + 2 * i}'
-            self._step(lambda nme=nme, a=cur: ops.linear(zb[a], P[nme + '.weight'], P[nme + '.bias'], act_out=ops.ACT_SILU,
-                                                        out=zb[1 - a]))
+            self._linear_rows(zb[cur], zd, P[nme + '.weight'], P[nme + '.bias'], zb[1 - cur], act_in=ops.ACT_SILU)
             cur = 1 - cur
-        self.zemb = zb[cur]
+        self.zemb_pre = zb[cur]                          # pre-activation; SiLU is folded into the style GEMM's prologue
         temb0 = torch.empty(N, nf, device=dev)
         temb1 = torch.empty(N, 4 * nf, device=dev)
         self.temb = torch.empty(N, 4 * nf, device=dev)
         self._step(lambda: ops.timestep_embedding(self.t_in, nf, out=temb0))
-        self._step(lambda: ops.linear(temb0, P['all_modules.0.weight'], P['all_modules.0.bias'], out=temb1))
-        self._step(lambda: ops.linear(temb1, P['all_modules.1.weight'], P['all_modules.1.bias'], act_in=ops.ACT_SILU, out=self.temb))
-        self._linear_rows(self.zemb, zd, self._w_style, self._b_style, self.style_all)
+        self._linear_rows(temb0, nf, P['all_modules.0.weight'], P['all_modules.0.bias'], temb1)
+        self._linear_rows(temb1, 4 * nf, P['all_modules.1.weight'], P['all_modules.1.bias'], self.temb, act_in=ops.ACT_SILU)
+        self._linear_rows(self.zemb_pre, zd, self._w_style, self._b_style, self.style_all, act_in=ops.ACT_SILU)
         self._linear_rows(self.temb, 4 * nf, self._w_dense, self._b_dense, self.dense_all, act_in=ops.ACT_SILU)
         self._keep.append((zb, temb0, temb1))
 
@@ -374,7 +374,7 @@ class GeneratorEngine(_EngineBase):
         self._conv(3 * C, [ops.conv_src(X.buf, C, ops.TAPS_1X1, scale=sc, shift=sh)], H, W, qkv, bind_qkv,
                    out_mode=ops.OUT_NHWC, bias=bqkv)
         # per-image K operand: B[co = key t][ci = channel]
-        wk = ops.ConvWeights(T, [(C, 1)], self.dev, precision=self.prec, batch=N)
+        wk = ops.ConvWeights(T, [(C, 1)], self.dev, precision=self.prec, batch=N, m_rows=N * T)
         self._step(lambda: wk.pack_segment(0, qkv, C, 3 * C, 1, 0, w_batch_stride=T * 3 * C, elem_offset=C))
         s = torch.zeros(N, T, Tp, device=self.dev)
         d = ops.build_conv_desc(wk, [ops.conv_src(qkv, C, ops.TAPS_1X1, padded=False, pitch=3 * C)], N, 1, T, s,
@@ -383,7 +383,7 @@ class GeneratorEngine(_EngineBase):
         p = torch.zeros(N, T, Tp, device=self.dev)
         self._step(lambda: ops.softmax_rows(s, p, N * T, T, Tp, Tp))
         # per-image V operand: B[co = channel][ci = key t] = v[t][c]
-        wv = ops.ConvWeights(C, [(Tp, 1)], self.dev, precision=self.prec, batch=N)
+        wv = ops.ConvWeights(C, [(Tp, 1)], self.dev, precision=self.prec, batch=N, m_rows=N * T)
         self._step(lambda: wv.pack_segment(0, qkv, T, 1, 3 * C, 0, w_batch_stride=T * 3 * C, elem_offset=2 * C))
         o = torch.zeros(N, T, C, device=self.dev)
         d2 = ops.build_conv_desc(wv, [ops.conv_src(p, Tp, ops.TAPS_1X1, padded=False)], N, 1, T, o, out_mode=ops.OUT_NHWC,
