@@ -66,7 +66,9 @@ def test_fused_bias_act(ops):
 
 
 @pytest.mark.parametrize('n,c,h,act,ada', [(4, 128, 32, 1, True), (2, 256, 16, 0, False), (3, 384, 8, 1, True),
-                                           (2, 12, 5, 0, True), (2, 64, 64, 1, True)])
+                                           (2, 12, 5, 0, True), (2, 64, 64, 1, True),
+                                           # slabs split over thread-block clusters: 256 KB -> 8 CTAs, 1 MB -> 16 CTAs
+                                           (2, 64, 128, 1, True), (2, 128, 128, 0, False), (1, 64, 256, 1, True)])
 def test_groupnorm_fwd_bwd(ops, n, c, h, act, ada):
     x = seeded((n, c, h, h), 7) * 2 + 0.5
     G = O.num_groups(c)
@@ -138,6 +140,15 @@ def test_layout_roundtrip_and_fir(ops):
     assert O.rel_l2(ops.from_pnhwc(up).cpu(), O.upsample_2d(tr)) < 1e-5
     dn = ops.fir_pnhwc(xp, 2, ops.alloc_pnhwc(2, 4, 4, 32, DEV))
     assert O.rel_l2(ops.from_pnhwc(dn).cpu(), O.downsample_2d(x)) < 1e-5
+    # several tiles per image with partial edge tiles (24 -> 48 = 3 x 16, 24 -> 12 = 8 + 4) and two 32-channel blocks
+    x2 = seeded((2, 64, 24, 24), 26); sc2 = 0.5 + torch.rand(2, 64, generator=torch.Generator().manual_seed(3)); sh2 = seeded((2, 64), 27, 0.3)
+    xp2 = ops.to_pnhwc(x2.to(DEV))
+    tr2 = F.silu(x2 * sc2[:, :, None, None] + sh2[:, :, None, None])
+    up2 = ops.fir_pnhwc(xp2, 1, ops.alloc_pnhwc(2, 48, 48, 64, DEV), sc2.to(DEV), sh2.to(DEV), ops.ACT_SILU)
+    assert O.rel_l2(ops.from_pnhwc(up2).cpu(), O.upsample_2d(tr2)) < 1e-5
+    assert float(up2[:, 0].abs().max()) == 0 and float(up2[:, :, -1].abs().max()) == 0
+    dn2 = ops.fir_pnhwc(xp2, 2, ops.alloc_pnhwc(2, 12, 12, 64, DEV), sc2.to(DEV), sh2.to(DEV), ops.ACT_SILU)
+    assert O.rel_l2(ops.from_pnhwc(dn2).cpu(), O.downsample_2d(tr2)) < 1e-5
     # mode 3: pad(2,2) FIR stored space-to-depth: cell (i,j), block (py,px) = fir[2i+py][2j+px]
     s2d = ops.fir_pnhwc(xp, 3, torch.zeros(2, 4 + 3, 4 + 3, 128, device=DEV))
     k = torch.from_numpy(O.setup_fir_kernel([1, 3, 3, 1]))
