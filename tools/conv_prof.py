@@ -30,9 +30,8 @@ def run(n, cin, cout, h, k, msub=0, affine=True, prec=3, nt256=1, stats=True):
     pv = prof.cpu().tolist()
     print(f'conv {cin}->{cout} {k}x{k} @{h}px n={n} msub={msub} prec={prec} nt256={nt256} stats={stats}: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s')
     print('   ' + '  '.join(f'{a}={b}' for a, b in zip(names, pv)))
+run(64, 256, 768, 16, 1)
+run(64, 256, 256, 16, 1)
 run(64, 128, 128, 32, 3)
-run(64, 128, 128, 32, 3, stats=False)
-run(64, 256, 256, 16, 3)
-run(64, 256, 256, 16, 3, stats=False)
 run(64, 256, 256, 8, 3)
-run(64, 256, 256, 8, 3, nt256=3)
+run(64, 256, 256, 4, 3)

@@ -28,3 +28,8 @@ print('total device time per step (ms):', tot / 2 / 1e3)
 for e in rows[:40]:
     if e.self_device_time_total > 0:
         print(f'{e.self_device_time_total/2/1e3:9.3f} ms x{e.count//2:5d}  {e.key[:100]}')
+print('--- by launch count ---')
+kern = [e for e in ev if e.self_device_time_total > 0 and not e.key.endswith('Fn') and not e.key.endswith('Backward') and not e.key.startswith('aten::')]
+for e in sorted(kern, key=lambda e: -e.count)[:28]:
+    print(f'x{e.count//2:5d} {e.self_device_time_total/2/1e3:8.3f} ms  {e.key[:110]}')
+print('kernel launches per step:', sum(e.count for e in kern) // 2)
