@@ -567,8 +567,8 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
     long long t_prod0 = 0, w_emptyA = 0;
     for (int tile = tile_first; tile < tile_end; tile += tile_stride, ++it) {
       set_tile(tile);
-      prof_on = (p.prof != nullptr) && it == 0 && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0;
-      t_prod0 = clock64();
+      prof_on = (p.prof != nullptr) && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0;
+      if (it == 0) t_prod0 = clock64();
     float cur[IMAX][8], nxt[IMAX][8];
     int off_c[IMAX], nn_c[IMAX], off_n[IMAX], nn_n[IMAX];
     int s_cur = 0, kb_cur = 0;
@@ -687,6 +687,10 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
     }
     // last tile of a persistent CTA: nothing is left to produce, so the producer warps take two thirds of its epilogue
     // (outside the tile loop: the register pipeline of the producer loop is dead here)
+    if (PERSIST && prof_on && tid == 0) {
+      p.prof[0] = clock64() - t_prod0;   // producer loops of all tiles of this CTA
+      p.prof[1] = w_emptyA;              // ... of which waiting for a free A stage
+    }
     if (PERSIST && it > 0) run_epilogue(it - 1, warp & 3, 1 + (warp >> 2), 3, false);
   } else if (warp < kEpiWarp0) {
     // WG2: the two single-thread roles (+ two idle warps in the persistent layout); their registers go to the producers
@@ -733,14 +737,14 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
       constexpr uint32_t b_kk16 = (2u * NT * 16u) >> 4;
       const uint32_t a_sub16 = (uint32_t)p.sub_stride >> 4;
       uint32_t bi = 0, ga = 0;                         // B / A stages consumed so far (ring positions across tiles)
-      long long w_fullA = 0, w_fullB = 0;
+      long long w_fullA = 0, w_fullB = 0, w_accE = 0;
       const long long t_m0 = clock64();
       int it = 0;
       for (int tile = tile_first; tile < tile_end; tile += tile_stride, ++it) {
       const int ab = PERSIST ? (it & 1) : 0;
       const uint32_t tmem_acc = tmem_base + (uint32_t)(ab * ACC_COLS);
       // the epilogue of the tile that used this accumulator set two iterations ago must have drained it
-      mbar_wait(accEmpty(ab), (PERSIST ? ((it >> 1) & 1) : 0) ^ 1);
+      { const long long tw = clock64(); mbar_wait(accEmpty(ab), (PERSIST ? ((it >> 1) & 1) : 0) ^ 1); w_accE += clock64() - tw; }
       tc_fence_after();
       uint32_t acc = 0;
       int s_m = 0, kb_m = 0;
@@ -793,6 +797,8 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
           p.prof[6] = clock64() - t_m0;  // MMA issue loop total
           p.prof[7] = w_fullA;           // ... waiting for A
           p.prof[8] = w_fullB;           // ... waiting for B
+          p.prof[9] = w_accE;            // ... waiting for the epilogue to drain an accumulator set (persistent)
+          p.prof[10] = it;               // tiles run by this CTA
         }
       }
       __syncwarp();
@@ -802,10 +808,17 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
     // =================================== epilogue warps (persistent variant) ===================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
     int it = 0;
+    long long w_accF = 0;
+    const long long t_e0 = clock64();
     for (int tile = tile_first; tile < tile_end; tile += tile_stride, ++it) {
       set_tile(tile);
       const bool last = tile + tile_stride >= tile_end;
+      { const long long tw = clock64(); mbar_wait(accFull(it & 1), (it >> 1) & 1); w_accF += clock64() - tw; }
       run_epilogue(it, warp & 3, 0, last ? 3 : 1, true);
+    }
+    if (p.prof != nullptr && blockIdx.x == gridDim.x / 2 && warp == kEpiWarp0 && lane == 0) {
+      p.prof[11] = clock64() - t_e0;   // epilogue warps: whole tile loop
+      p.prof[12] = w_accF;             // ... of which waiting for a finished accumulator set
     }
   }
 
@@ -1036,7 +1049,7 @@ extern "C" int ddg_conv2d_fwd(const ddg_conv_desc* c, cudaStream_t stream) {
   // Persistent variant: more tiles than SMs, so every CTA runs >= 2 tiles back to back and the epilogue of tile i overlaps
   // the mainloop of tile i+1 (two accumulator sets in TMEM: msub * nt <= 256 columns each).
   bool persist = false;
-  if (g_persist && c->batch_rows == 0 && c->debug_prof == nullptr) {
+  if (g_persist && c->batch_rows == 0) {
     auto tiles_for = [&](int ms) -> long {
       return (tile2d ? (long)d.N * (d.Hout / (16 * ms)) * (d.Wout / 8) : ((long)d.Mtotal + 128 * ms - 1) / (128 * ms)) * n_tiles;
     };

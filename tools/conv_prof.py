@@ -4,7 +4,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'denoising-diffu
 import torch
 from ddgan_b200 import ops
 dev = 'cuda'
-names = ['prod_total', 'prod_wait_emptyA', 'prod_wait_acc', 'epilogue', 'loader_total', 'loader_wait_emptyB', 'mma_total', 'mma_wait_A', 'mma_wait_B']
+names = ['prod_total', 'prod_wait_emptyA', 'prod_wait_acc', 'epilogue', 'loader_total', 'loader_wait_emptyB', 'mma_total', 'mma_wait_A', 'mma_wait_B', 'mma_wait_accEmpty', 'tiles', 'epi_total', 'epi_wait_accFull']
 def run(n, cin, cout, h, k, msub=0, affine=True, prec=3, nt256=1, stats=True):
     from ddgan_b200._lib import lib
     lib().ddg_conv_set_nt256(nt256)
@@ -30,8 +30,6 @@ def run(n, cin, cout, h, k, msub=0, affine=True, prec=3, nt256=1, stats=True):
     pv = prof.cpu().tolist()
     print(f'conv {cin}->{cout} {k}x{k} @{h}px n={n} msub={msub} prec={prec} nt256={nt256} stats={stats}: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s')
     print('   ' + '  '.join(f'{a}={b}' for a, b in zip(names, pv)))
-run(64, 256, 768, 16, 1)
-run(64, 256, 256, 16, 1)
 run(64, 128, 128, 32, 3)
-run(64, 256, 256, 8, 3)
-run(64, 256, 256, 4, 3)
+run(64, 256, 256, 32, 3)
+run(64, 256, 768, 16, 1)
