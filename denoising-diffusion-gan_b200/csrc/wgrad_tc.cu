@@ -90,6 +90,7 @@ struct WgradDev {
   int xpitch_b;        // X window chunk pitch in bytes
   int splits_pad;      // split slots per (co, ci, tap-group) block, a multiple of the cluster size; blockIdx.z = grp * splits_pad + split
   int cs;              // cluster size along z: the CTAs of one cluster hold partial sums of the same dW block
+  float gain;          // multiplies the block before it is added to dW
   int order;           // dW walk of the final reduction: 0 = taps fastest, then ci, then co (conv layouts); 1 = co fastest (NIN [in][out])
 };
 
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const __grid_con
           for (int f = lane; f < rlen; f += 32) {              // f walks (ci, tap) with the tap fastest, as dW does
             const int ci_l = f / ntl, tl = f - ci_l * ntl;
             const int ci = ci0 + ci_l;
-            if (ci < p.Cin_real) atomicAdd(dst + (size_t)ci * p.s_ci + (size_t)(t0 + tl) * p.s_tap, T[tl * NCI + ci_l]);
+            if (ci < p.Cin_real) atomicAdd(dst + (size_t)ci * p.s_ci + (size_t)(t0 + tl) * p.s_tap, p.gain * T[tl * NCI + ci_l]);
           }
         }
       } else {
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const __grid_con
           float* dst = p.dw + (size_t)ci * p.s_ci + (size_t)(t0 + tl) * p.s_tap;
           for (int b = lane; b < rlen; b += 32) {
             const int co = co0 + b;
-            if (co < p.Cout) atomicAdd(dst + (size_t)co * p.s_co, T[b]);
+            if (co < p.Cout) atomicAdd(dst + (size_t)co * p.s_co, p.gain * T[b]);
           }
         }
       }
@@ -465,6 +466,7 @@ extern "C" int ddg_conv2d_wgrad(const ddg_wgrad_desc* c, cudaStream_t stream) {
   d.ntaps = c->ntaps;
   for (int t = 0; t < c->ntaps; ++t) d.tapoff[t] = c->tap_dr[t] * c->Wp + c->tap_ds[t];
   d.s_co = c->s_co; d.s_ci = c->s_ci; d.s_tap = c->s_tap;
+  d.gain = c->gain == 0.f ? 1.f : c->gain;
   const int prec = c->precision == 1 ? 1 : 3;
   if (c->Cin_pad % 128 == 0) {
     // one tap row per CTA: 3x3 -> 3 groups of 3, 2x2 -> 2 groups of 2, 1x1 -> 1 group

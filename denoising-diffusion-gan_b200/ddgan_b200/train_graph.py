@@ -57,13 +57,13 @@ class FromPnhwcFn(Function):
 # ------------------------------------------------------------------------------------------------------------------
 # convolution family
 # ------------------------------------------------------------------------------------------------------------------
-def conv_spec(w_shape, taps, n, hout, wout, cpad_in, s_co, s_ci, s_tap, cout, cin, hp=None, wp=None, out_nchw=False, prec=3):
+def conv_spec(w_shape, taps, n, hout, wout, cpad_in, s_co, s_ci, s_tap, cout, cin, hp=None, wp=None, out_nchw=False, prec=3, out_scale=1.0):
     return SimpleNamespace(w_shape=tuple(w_shape), taps=list(taps), n=n, hout=hout, wout=wout, hp=hp or hout + 2,
                            wp=wp or wout + 2, cpad_in=cpad_in, s_co=s_co, s_ci=s_ci, s_tap=s_tap, cout=cout, cin=cin,
-                           out_nchw=out_nchw, prec=prec, cpad_out=ops.pad_c(cout))
+                           out_nchw=out_nchw, prec=prec, cpad_out=ops.pad_c(cout), out_scale=float(out_scale))
 
 
-def _conv_forward(x, w, bias, addvec, sp):
+def _conv_forward(x, w, bias, addvec, sp, res=None):
     m_rows = sp.n * sp.hp * sp.wp if len(sp.taps) > 1 else sp.n * sp.hout * sp.wout
     cw = ops.ConvWeights(sp.cout, [(sp.cpad_in, len(sp.taps))], x.device, precision=sp.prec, m_rows=m_rows)
     cw.pack_segment(0, w, sp.cin, sp.s_co, sp.s_ci, sp.s_tap)
@@ -74,7 +74,8 @@ def _conv_forward(x, w, bias, addvec, sp):
         out = ops.alloc_pnhwc(sp.n, sp.hout, sp.wout, sp.cpad_out, x.device, full=(sp.cout != sp.cpad_out))
         mode, out_c = ops.OUT_PNHWC, sp.cpad_out
     ops.conv2d_fused(cw, [ops.conv_src(x, sp.cpad_in, sp.taps)], sp.n, sp.hout, sp.wout, out, out_mode=mode, out_c=out_c,
-                     hp=sp.hp, wp=sp.wp, bias=bias, addvec=addvec, addvec_stride=(addvec.shape[1] if addvec is not None else 0))
+                     hp=sp.hp, wp=sp.wp, bias=bias, addvec=addvec, addvec_stride=(addvec.shape[1] if addvec is not None else 0),
+                     res=res, out_scale=sp.out_scale)
     return out
 
 
@@ -90,16 +91,19 @@ def _crop(t, hp, wp):
 
 
 class ConvFn(Function):
-    """y = conv(x; w) + bias + addvec[n, c]   (x, y PNHWC; y NCHW when sp.out_nchw)."""
+    """y = sp.out_scale * (conv(x; w) + bias + addvec[n, c] + res)   (x, y, res PNHWC; y NCHW when sp.out_nchw).
+    The scale and the residual ride in the conv epilogue (layerspp.py:307-309 "(x + h) / sqrt(2)"); in the backward the scale is
+    the epilogue scale of the dgrad launch and the gain of the wgrad reduction, so it never costs an elementwise pass."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, addvec, sp):
+    def forward(ctx, x, w, bias, addvec, res, sp):
         x = x.contiguous()
         w = w.contiguous()
         ctx.sp = sp
-        ctx.has_bias, ctx.has_addvec = bias is not None, addvec is not None
+        ctx.has_bias, ctx.has_addvec, ctx.has_res = bias is not None, addvec is not None, res is not None
         ctx.save_for_backward(x, w)
-        return _conv_forward(x, w, bias, addvec.contiguous() if addvec is not None else None, sp)
+        return _conv_forward(x, w, bias, addvec.contiguous() if addvec is not None else None, sp,
+                             res.contiguous() if res is not None else None)
 
     @staticmethod
     def backward(ctx, dy):
@@ -112,18 +116,20 @@ class ConvFn(Function):
         dw = WgradFn.apply(x, dyc, sp) if ctx.needs_input_grad[1] else None
         need_db = ctx.has_bias and ctx.needs_input_grad[2]
         need_dav = ctx.has_addvec and ctx.needs_input_grad[3]
-        db = dav = None
+        db = dav = dres = None
         if need_db or need_dav:
             if torch.is_grad_enabled() and dyc.requires_grad:
                 # create_graph pass: keep the reductions differentiable
-                db = dyc.sum(dim=(0, 1, 2))[:sp.cout] if need_db else None
-                dav = dyc.sum(dim=(1, 2))[:, :sp.cout] if need_dav else None
+                db = dyc.sum(dim=(0, 1, 2))[:sp.cout] * sp.out_scale if need_db else None
+                dav = dyc.sum(dim=(1, 2))[:, :sp.cout] * sp.out_scale if need_dav else None
             else:
                 # one streaming pass of the PNHWC reduction kernel gives the per-(sample, channel) sums both gradients need
-                nc = ops.stats_fwd(dyc)[:, :sp.cout, 0]
+                nc = ops.stats_fwd(dyc)[:, :sp.cout, 0] * sp.out_scale
                 dav = nc.float() if need_dav else None
                 db = nc.sum(0).float() if need_db else None
-        return dx, dw, db, dav, None
+        if ctx.has_res and ctx.needs_input_grad[4]:
+            dres = dyc * sp.out_scale if sp.out_scale != 1.0 else dyc
+        return dx, dw, db, dav, dres, None
 
 
 class DgradFn(Function):
@@ -143,7 +149,7 @@ class DgradFn(Function):
         cw.pack_segment(0, w, sp.cout, sp.s_ci, sp.s_co, sp.s_tap)   # roles of co / ci swapped
         dx = ops.alloc_pnhwc(sp.n, sp.hp - 2, sp.wp - 2, sp.cpad_in, dy.device, full=False)
         taps = [(-dr, -ds) for dr, ds in sp.taps]
-        ops.conv2d_fused(cw, [ops.conv_src(dye, cy, taps)], sp.n, sp.hp - 2, sp.wp - 2, dx)
+        ops.conv2d_fused(cw, [ops.conv_src(dye, cy, taps)], sp.n, sp.hp - 2, sp.wp - 2, dx, out_scale=sp.out_scale)
         if sp.cin < sp.cpad_in:
             dx[..., sp.cin:] = 0
         return dx
@@ -156,7 +162,7 @@ class DgradFn(Function):
         g_dy = g_w = None
         if ctx.needs_input_grad[0]:
             spf = SimpleNamespace(**{**vars(sp), 'out_nchw': False})
-            g_dy = ConvFn.apply(ggx, w, None, None, spf)
+            g_dy = ConvFn.apply(ggx, w, None, None, None, spf)
         if ctx.needs_input_grad[1]:
             g_w = WgradFn.apply(ggx, dy, sp)
         return g_dy, g_w, None
@@ -174,7 +180,7 @@ class WgradFn(Function):
         dye = _embed(dy, sp.hp, sp.wp).contiguous()
         dw = torch.zeros(sp.w_shape, device=x.device)
         ops.conv_wgrad(x, dye, dw, sp.n, sp.hp, sp.wp, sp.cout, sp.cin, sp.cpad_in, sp.taps, sp.s_co, sp.s_ci, sp.s_tap,
-                       precision=sp.prec)
+                       precision=sp.prec, gain=sp.out_scale)
         return dw
 
     @staticmethod
@@ -187,36 +193,36 @@ class WgradFn(Function):
             g_x = DgradFn.apply(dy, gdw, sp)
         if ctx.needs_input_grad[1]:
             spf = SimpleNamespace(**{**vars(sp), 'out_nchw': False})
-            g_dy = _crop(ConvFn.apply(x, gdw, None, None, spf), dy.shape[1], dy.shape[2])
+            g_dy = _crop(ConvFn.apply(x, gdw, None, None, None, spf), dy.shape[1], dy.shape[2])
         return g_x, g_dy, None
 
 
-def conv3x3(x, w, b, n, h, wd, addvec=None, out_nchw=False, prec=3):
+def conv3x3(x, w, b, n, h, wd, addvec=None, out_nchw=False, prec=3, res=None, out_scale=1.0):
     """nn.Conv2d(k=3, s=1, p=1) on PNHWC; w [Cout, Cin, 3, 3] (zero-padded along Cin to x's channel count if needed)."""
     cout, cin = w.shape[0], w.shape[1]
     cp = x.shape[-1]
     if cin < cp:
         w = F.pad(w, (0, 0, 0, 0, 0, cp - cin))
-    sp = conv_spec(w.shape, ops.TAPS_3X3, n, h, wd, cp, cp * 9, 9, 1, cout, cp, out_nchw=out_nchw, prec=prec)
-    return ConvFn.apply(x, w, b, addvec, sp)
+    sp = conv_spec(w.shape, ops.TAPS_3X3, n, h, wd, cp, cp * 9, 9, 1, cout, cp, out_nchw=out_nchw, prec=prec, out_scale=out_scale)
+    return ConvFn.apply(x, w, b, addvec, res, sp)
 
 
-def conv1x1(x, w, b, n, h, wd, prec=3):
+def conv1x1(x, w, b, n, h, wd, prec=3, res=None, out_scale=1.0):
     """1x1 conv; w [Cout, Cin, 1, 1] or [Cout, Cin]."""
     cout, cin = w.shape[0], w.shape[1]
     cp = x.shape[-1]
     w2 = w.reshape(cout, cin)
     if cin < cp:
         w2 = F.pad(w2, (0, cp - cin))
-    sp = conv_spec(w2.shape, ops.TAPS_1X1, n, h, wd, cp, cp, 1, 0, cout, cp, prec=prec)
-    return ConvFn.apply(x, w2, b, None, sp)
+    sp = conv_spec(w2.shape, ops.TAPS_1X1, n, h, wd, cp, cp, 1, 0, cout, cp, prec=prec, out_scale=out_scale)
+    return ConvFn.apply(x, w2, b, None, res, sp)
 
 
-def nin(x, W, b, n, h, wd, prec=3):
+def nin(x, W, b, n, h, wd, prec=3, res=None, out_scale=1.0):
     """layers.py:489-512: weight stored [in, out]."""
     cin, cout = W.shape
-    sp = conv_spec(W.shape, ops.TAPS_1X1, n, h, wd, x.shape[-1], 1, cout, 0, cout, cin, prec=prec)
-    return ConvFn.apply(x, W, b, None, sp)
+    sp = conv_spec(W.shape, ops.TAPS_1X1, n, h, wd, x.shape[-1], 1, cout, 0, cout, cin, prec=prec, out_scale=out_scale)
+    return ConvFn.apply(x, W, b, None, res, sp)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -427,11 +433,12 @@ def generator_forward(mod, x, time_cond, z):
         hh = adagn(hh, h, w, pn + 'GroupNorm_1')
         if drop > 0:
             hh = F.dropout(hh, drop, True)
-        hh = conv3x3(hh, P[pn + 'Conv_1.weight'], P[pn + 'Conv_1.bias'], N, h, w, prec=prec)
         if cin != cout or m['up'] or m['down']:
             xs = conv1x1(xs, P[pn + 'Conv_2.weight'], P[pn + 'Conv_2.bias'], N, h, w, prec=prec)
-        out = xs + hh
-        return (out * RSQRT2 if cfg.skip_rescale else out), h, w
+        # (skip + h) / sqrt(2) in Conv_1's epilogue
+        out = conv3x3(hh, P[pn + 'Conv_1.weight'], P[pn + 'Conv_1.bias'], N, h, w, prec=prec, res=xs,
+                      out_scale=RSQRT2 if cfg.skip_rescale else 1.0)
+        return out, h, w
 
     def attn(m, t, h, w):
         pn = f"all_modules.{m['idx']}."
@@ -443,9 +450,7 @@ def generator_forward(mod, x, time_cond, z):
         a = torch.softmax(torch.bmm(q, k.transpose(1, 2)) * (int(c) ** (-0.5)), dim=-1)
         o = torch.bmm(a, v).reshape(N, h, w, c)
         o = F.pad(o, (0, 0, 1, 1, 1, 1))
-        o = nin(o, P[pn + 'NIN_3.W'], P[pn + 'NIN_3.b'], N, h, w, prec)
-        out = t + o
-        return out * RSQRT2 if cfg.skip_rescale else out
+        return nin(o, P[pn + 'NIN_3.W'], P[pn + 'NIN_3.b'], N, h, w, prec, res=t, out_scale=RSQRT2 if cfg.skip_rescale else 1.0)
 
     def pyramid_down(m, pyr, hcur, h, w):
         """conv_downsample_2d + bias, then (pyramid + h)/sqrt2 (ncsnpp...:343-350); h, w = input size of pyr."""
@@ -464,10 +469,9 @@ def generator_forward(mod, x, time_cond, z):
                         if r < 3 and s_ < 3:
                             w2[:, py, px, :cin, dy, dx] = wt[:, :, r, s_]
         w2 = w2.reshape(cout, 4 * cp, 4)
-        sp = conv_spec(w2.shape, ops.TAPS_2X2, N, ho, wo, 4 * cp, 4 * cp * 4, 4, 1, cout, 4 * cp, hp=ho + 3, wp=wo + 3, prec=prec)
-        y = ConvFn.apply(s2d, w2, P[pn + '.bias'], None, sp)
-        out = y + hcur
-        return out * RSQRT2 if cfg.skip_rescale else out
+        sp = conv_spec(w2.shape, ops.TAPS_2X2, N, ho, wo, 4 * cp, 4 * cp * 4, 4, 1, cout, 4 * cp, hp=ho + 3, wp=wo + 3, prec=prec,
+                       out_scale=RSQRT2 if cfg.skip_rescale else 1.0)
+        return ConvFn.apply(s2d, w2, P[pn + '.bias'], None, hcur, sp)
 
     mods = arch.ncsnpp_modules(cfg)
     xin = x if cfg.centered else 2 * x - 1.0
@@ -539,9 +543,8 @@ def discriminator_forward(mod, x, t, x_t):
         xs = h
         if ds:
             o, xs, cur = fir_down(o), fir_down(xs), cur // 2
-        o = conv3x3(o, P[pn + 'conv2.0.weight'], P[pn + 'conv2.0.bias'], N, cur, cur, prec=prec)
         sk = conv1x1(xs, P[pn + 'skip.0.weight'], None, N, cur, cur, prec=prec)
-        h = (o + sk) * RSQRT2
+        h = conv3x3(o, P[pn + 'conv2.0.weight'], P[pn + 'conv2.0.bias'], N, cur, cur, prec=prec, res=sk, out_scale=RSQRT2)
     # minibatch stddev (discriminator.py:150-158) on the interior, appended as one extra (32-padded) channel group
     c = h.shape[-1]
     group = min(N, mod.stddev_group)

@@ -172,6 +172,7 @@ typedef struct {
   int8_t tap_dr[9]; int8_t tap_ds[9];
   long s_co, s_ci, s_tap;
   int precision;
+  float gain;                  /* dw += gain * (...); 0 is read as 1 (the adjoint of a conv whose epilogue applies out_scale) */
 } ddg_wgrad_desc;
 int ddg_conv2d_wgrad(const ddg_wgrad_desc* desc, cudaStream_t stream);
 
