@@ -9,6 +9,8 @@ from ddgan_b200.engine import GeneratorEngine
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 prec = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 cfg = arch.make_config()
+if len(sys.argv) > 3 and sys.argv[3] == 'hq256':
+    cfg = arch.make_config(image_size=256, num_channels_dae=64, ch_mult=(1, 1, 2, 2, 4, 4), n_mlp=3, num_timesteps=2, ngf=64)
 eng = GeneratorEngine(cfg, B, 'cuda', precision=prec)
 sd = {k: torch.randn(s) * (0.05 if len(s) > 1 else 0.1) + (1.0 if (len(s) == 1 and k.endswith('weight')) else 0.0) for k, s in eng.shapes.items()}
 eng.load_state_dict(sd)
