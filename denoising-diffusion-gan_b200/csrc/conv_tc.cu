@@ -21,6 +21,11 @@
 //     tcgen05.mma.cta_group::1.kind::f16; tcgen05.commit releases the smem stages and signals the epilogue.
 //   * Epilogue: tcgen05.ld -> + bias[c] + addvec[n,c] -> (+ residual) * out_scale -> act -> store (padded NHWC /
 //     NHWC / NCHW) and per-(n,c) sum / sum-of-squares accumulation for the GroupNorm that consumes the output.
+//   * Tiles: 2-D (16*MSUB image rows x 8 columns, halo window (rows+2) x 10, SBO = 160 B) when H % 16 == 0 and W % 8 == 0,
+//     else linear over the padded pixel space.  One tile per CTA (10 warps, producers run the epilogue), or -- when there
+//     are more tiles than SMs -- the PERSIST variant: 16 warps, every CTA walks tiles b, b + grid, ..., two accumulator
+//     sets in TMEM and four dedicated epilogue warps overlap the epilogue of tile i with the mainloop of tile i + 1,
+//     setmaxnreg moves registers from the single-thread roles to the producer warpgroups.
 #include <cstdlib>
 #include "common.cuh"
 #include "ddgan_b200.h"

@@ -9,10 +9,13 @@
 // SBO = chunk pitch (next 8 channels) and LBO = 128 B (next 8 pixel rows), and a filter tap is again a start-address offset of
 // off(tap) rows.  dY is stored PNHWC with a zero border, so border positions contribute nothing and need no masking.
 //
-// One CTA owns a (128 output channels) x (32 input channels) x (all taps) block of dW -- 9 x 32 = 288 fp32 TMEM columns --
-// and a slice of the pixel space (split-K); it streams pixel tiles of 128 rows through a 2-stage smem ring (producer warps
-// convert fp32 -> bf16 hi/lo; BF16x3 as in the forward), accumulates in TMEM across all its tiles, and finally adds its
-// block into dW with fp32 reductions (red.global.add).
+// One CTA owns a (128 output channels) x (128 input channels) x (one tap row, <= 3 taps) block of dW -- 384 fp32 TMEM columns;
+// 32 input channels x all taps for narrow inputs -- and a slice of the pixel space (split-K, factor from a cycle model on the
+// host); it streams pixel tiles of 64 rows through a 3-stage smem ring (producer warps convert fp32 -> bf16 hi/lo; BF16x3 as in
+// the forward) and accumulates in TMEM across all its tiles.  The partial blocks are then staged in shared memory (the operand
+// ring is dead by then), summed across a 2-CTA cluster with vector DSMEM loads, re-read in dW order and added to dW with
+// red.global.add so that neighbouring lanes share sectors.  UMMA descriptor addresses are masked to the CTA-local offset:
+// inside a cluster the shared window of rank r starts at r << 24.
 #include <cstdlib>
 #include "common.cuh"
 #include "ddgan_b200.h"
