@@ -888,6 +888,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
 struct Variant { int msub, nt, kb; };
 
 static int g_small_nt64 = 1;
+static thread_local int g_last_info[4] = {0, 0, 0, 0};   // msub, nt, persistent, CTAs of the last launch
 static int g_persist = getenv("DDG_CONV_NO_PERSIST") ? 0 : 1;   // persistent variant (epilogue overlapped with the next tile's mainloop) when tiles > SMs
 static int num_sms() {
   static int n = 0;
@@ -924,9 +925,12 @@ static int launch_conv(ConvDev& d, int n_tiles, cudaStream_t stream) {
   if (d.batch_rows > 0) grid = dim3((d.batch_rows + Cfg::MT - 1) / Cfg::MT, n_tiles, d.Mtotal / d.batch_rows);
   d.tiles_m = (int)grid.x;
   d.n_tiles = n_tiles;
+  g_last_info[0] = MSUB; g_last_info[1] = NT; g_last_info[2] = PERSIST ? 1 : 0;
+  g_last_info[3] = (int)(grid.x * grid.y * grid.z);
   if (PERSIST) {
     const long total = (long)grid.x * n_tiles;
     grid = dim3((unsigned)(total < num_sms() ? total : num_sms()));
+    g_last_info[3] = (int)grid.x;
     kern<<<grid, kThreadsPersist, smem, stream>>>(d);
   } else {
     kern<<<grid, kThreads, smem, stream>>>(d);
@@ -940,6 +944,13 @@ static int launch_conv(ConvDev& d, int n_tiles, cudaStream_t stream) {
 using namespace ddg;
 
 extern "C" int ddg_conv_tile_n(int cout, long m_rows) { return pick_nt(cout, m_rows); }
+extern "C" int ddg_conv_last_launch_info(int* msub, int* nt, int* persistent, int* grid_ctas) {
+  if (msub) *msub = g_last_info[0];
+  if (nt) *nt = g_last_info[1];
+  if (persistent) *persistent = g_last_info[2];
+  if (grid_ctas) *grid_ctas = g_last_info[3];
+  return DDG_OK;
+}
 // tuning switches (bring-up / A-B measurements): bit 0 = N=256 tiles, bit 1 = no N=64 on tiny levels, bit 2 = no persistent variant
 extern "C" int ddg_conv_set_nt256(int on) {
   const int old = g_nt256;

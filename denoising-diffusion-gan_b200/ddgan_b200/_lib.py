@@ -58,6 +58,7 @@ _SIGNATURES = {
     'ddg_fir_pnhwc': ([_P, _P, _P, _I, _P] + [_I] * 6 + [_F, _P], _I),
     'ddg_minibatch_stddev': ([_P, _P] + [_I] * 6 + [_P], _I),
     'ddg_spatial_sum': ([_P, _P] + [_I] * 5 + [_P], _I),
+    'ddg_conv_last_launch_info': ([_P, _P, _P, _P], _I),
     'ddg_zero_border': ([_P] + [_I] * 4 + [_P], _I),
     'ddg_softmax_rows': ([_P, _P, _L, _I, _I, _I, _P], _I),
     'ddg_conv_tile_n': ([_I, _L], _I),

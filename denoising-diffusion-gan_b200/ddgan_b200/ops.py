@@ -431,6 +431,13 @@ def conv_launch(desc: ConvDesc):
     check(lib().ddg_conv2d_fwd(C.byref(desc), stream()), 'conv2d_fwd')
 
 
+def conv_last_launch_info():
+    """(msub, nt, persistent, CTAs) of the last conv launch made from this thread."""
+    v = [C.c_int(0) for _ in range(4)]
+    check(lib().ddg_conv_last_launch_info(*[C.byref(a) for a in v]), 'conv_last_launch_info')
+    return tuple(a.value for a in v)
+
+
 def conv2d_fused(weights, srcs, n, hout, wout, out, **kw):
     d = build_conv_desc(weights, srcs, n, hout, wout, out, **kw)
     conv_launch(d)

@@ -157,6 +157,8 @@ int ddg_conv_pack_weights(const float* w, void* out, int cout, int cin_real, int
                           long s_tap, int flip_taps, int kb, int stage_offset, int total_stages, int precision, int nt, int batch,
                           long w_batch_stride, cudaStream_t stream);
 int ddg_conv2d_fwd(const ddg_conv_desc* desc, cudaStream_t stream);
+/* diagnostics: which kernel variant the last ddg_conv2d_fwd call on this host thread launched (tests assert on it) */
+int ddg_conv_last_launch_info(int* msub, int* nt, int* persistent, int* grid_ctas);
 
 /* Weight gradient of the same convolution (cuDNN wgrad in the reference's backward, ddgan.py:459-506):
  *   dw[co*s_co + ci*s_ci + tap*s_tap] += sum_q dy[q][co] * x[q + tap_dr*Wp + tap_ds][ci]   over the padded space [N][Hp][Wp]

@@ -251,6 +251,39 @@ def test_conv_tc_linear_and_2d_tilings_agree(ops):
         assert err < 2e-5 and e1 < 5e-5 and e2 < 5e-5
 
 
+def test_conv_tc_persistent_variants(ops):
+    """More tiles than SMs selects the persistent kernel (several tiles per CTA, TMEM double-buffered epilogue, dedicated epilogue
+    warps, producers helping on the last tile).  Shapes are chosen per instantiation; tile counts are not multiples of the SM
+    count, so CTAs with different numbers of tiles coexist."""
+    # <1,128>: 20 * 8 = 160 tiles of 128 rows, fused 1x1 skip segment
+    err, e1, e2 = _conv_case(ops, 20, 64, 128, 32, 3, skip1x1=64)
+    assert err < 2e-5 and e1 < 5e-5 and e2 < 5e-5, (err, e1, e2)
+    assert ops.conv_last_launch_info()[:3] == (1, 128, 1), ops.conv_last_launch_info()
+    # <2,128>: 56 * 4 = 224 tiles of 256 rows
+    err, e1, e2 = _conv_case(ops, 56, 64, 128, 32, 3, affine=True, act=1)
+    assert err < 2e-5 and e1 < 5e-5 and e2 < 5e-5, (err, e1, e2)
+    assert ops.conv_last_launch_info()[:3] == (2, 128, 1), ops.conv_last_launch_info()
+    # <1,256>: 40 * 8 = 320 tiles, every epilogue feature (AdaGN prologue, temb add, residual, rescale, statistics)
+    err, e1, e2 = _conv_case(ops, 40, 128, 256, 32, 3, affine=True, act=1, res=True, temb=True)
+    assert err < 2e-5 and e1 < 5e-5 and e2 < 5e-5, (err, e1, e2)
+    assert ops.conv_last_launch_info()[:3] == (1, 256, 1), ops.conv_last_launch_info()
+    # <2,64> and <2,16> (NCHW + tanh-less output conv shape)
+    err, e1, e2 = _conv_case(ops, 64, 32, 64, 32, 3)
+    assert err < 2e-5 and e1 < 5e-5 and e2 < 5e-5, (err, e1, e2)
+    assert ops.conv_last_launch_info()[:3] == (2, 64, 1), ops.conv_last_launch_info()
+    err, _, _ = _conv_case(ops, 64, 32, 3, 32, 3, nchw=True)
+    assert err < 2e-5
+    assert ops.conv_last_launch_info()[:3] == (2, 16, 1), ops.conv_last_launch_info()
+    # 1x1 with three N tiles per M tile (the attention QKV projection shape)
+    err, e1, e2 = _conv_case(ops, 64, 64, 768, 16, 1, affine=True)
+    assert err < 2e-5 and e1 < 5e-5 and e2 < 5e-5, (err, e1, e2)
+    assert ops.conv_last_launch_info()[:3] == (1, 256, 1), ops.conv_last_launch_info()
+    # single-pass BF16 mode on the persistent path
+    err, _, _ = _conv_case(ops, 56, 64, 128, 32, 3, prec=1)
+    assert 1e-4 < err < 5e-3, err
+    assert ops.conv_last_launch_info()[:3] == (2, 128, 1), ops.conv_last_launch_info()
+
+
 def test_conv_tc_bf16_mode(ops):
     # BF16 mode: single-pass bf16 operands, fp32 accumulate.  Stated tolerance: 5e-3 relative L2 per op
     # (SURVEY.md section 7 hard part 1 measured 2.3e-3 for bf16 operands).

@@ -17,7 +17,8 @@ def seeded(shape, seed, scale=1.0):
     return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
 
 
-@pytest.mark.parametrize('n,cin,cout,h,k', [(2, 32, 64, 8, 3), (4, 64, 128, 16, 3), (3, 128, 32, 8, 1), (2, 256, 256, 4, 3), (8, 128, 128, 32, 3)])
+@pytest.mark.parametrize('n,cin,cout,h,k', [(2, 32, 64, 8, 3), (4, 64, 128, 16, 3), (3, 128, 32, 8, 1), (2, 256, 256, 4, 3), (8, 128, 128, 32, 3),
+                                            (32, 128, 128, 32, 3)])   # bench-scale: persistent fwd / dgrad kernels, clustered split-K wgrad
 def test_conv_grads_and_double_backward(n, cin, cout, h, k):
     from ddgan_b200 import train_graph as TG
     x = seeded((n, cin, h, h), 1); w = seeded((cout, cin, k, k), 2) / math.sqrt(cin * k * k); b = seeded((cout,), 3, 0.1)
@@ -42,6 +43,26 @@ def test_conv_grads_and_double_backward(n, cin, cout, h, k):
     assert O.rel_l2(gb.detach().cpu(), gb1) < 5e-5
     ggw, = torch.autograd.grad((gx ** 2).sum(), wd)
     assert O.rel_l2(ggw.cpu(), ggw_ref) < GTOL
+
+
+def test_conv_residual_and_rescale_in_epilogue():
+    """y = s * (conv(x) + b + res): the residual and the 1/sqrt(2) rescale ride in the conv epilogue; s is the dgrad launch's
+    epilogue scale and the wgrad reduction's gain (layerspp.py:305-310)."""
+    from ddgan_b200 import train_graph as TG
+    n, cin, cout, h, sc = 4, 64, 128, 16, 1.0 / math.sqrt(2.0)
+    x = seeded((n, cin, h, h), 61); w = seeded((cout, cin, 3, 3), 62) / math.sqrt(cin * 9); b = seeded((cout,), 63, 0.1)
+    r = seeded((n, cout, h, h), 64)
+    xr, wr, br, rr = [t.clone().requires_grad_(True) for t in (x, w, b, r)]
+    ref = (F.conv2d(xr, wr, br, padding=1) + rr) * sc
+    gy = seeded(tuple(ref.shape), 65)
+    g_ref = torch.autograd.grad((ref * gy).sum(), (xr, wr, br, rr))
+    xd, wd, bd, rd = [t.to(DEV).requires_grad_(True) for t in (x, w, b, r)]
+    y = TG.conv3x3(TG.ToPnhwcFn.apply(xd, cin), wd, bd, n, h, h, res=TG.ToPnhwcFn.apply(rd, cout), out_scale=sc)
+    yo = TG.FromPnhwcFn.apply(y, cout)
+    assert O.rel_l2(yo.detach().cpu(), ref.detach()) < 2e-5
+    g = torch.autograd.grad((yo * gy.to(DEV)).sum(), (xd, wd, bd, rd))
+    for a, e in zip(g, g_ref):
+        assert O.rel_l2(a.cpu(), e) < 5e-5
 
 
 def test_groupnorm_fir_linear_grads():
