@@ -65,6 +65,13 @@ def test_generator_cifar_vs_oracle(golden):
     assert O.rel_l2(y[2:].cpu(), golden['ncsnpp_cifar_out']) < TOL
 
 
+def test_generator_cifar_bench_batch_vs_oracle():
+    """The BASELINE workload size (batch 64): this is where the persistent conv kernels, N = 256 attention GEMMs and full-size
+    FIR tiles run; same 1e-4 gate against the CPU oracle."""
+    err, _ = _gen_case(O.cifar10_config(), 64, 12, capture=True)
+    assert err < TOL, err
+
+
 def test_generator_bf16_mode():
     # BF16 mode: stated tolerance 2e-2 relative L2 per generator forward (bf16 operands, fp32 accumulate).
     err, _ = _gen_case(O.tiny_config(), 3, 7, precision=1)
