@@ -37,6 +37,14 @@ class WgradDesc(C.Structure):
                 ('tap_ds', C.c_int8 * 9), ('s_co', C.c_long), ('s_ci', C.c_long), ('s_tap', C.c_long), ('precision', C.c_int), ('gain', C.c_float)]
 
 
+MLP_MAX_LAYERS = 8
+
+
+class MlpDesc(C.Structure):
+    _fields_ = [('W', C.c_void_p * MLP_MAX_LAYERS), ('b', C.c_void_p * MLP_MAX_LAYERS), ('dims', C.c_int * (MLP_MAX_LAYERS + 1)),
+                ('nlayers', C.c_int), ('pixel_norm', C.c_int), ('act', C.c_int)]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_long, C.c_float
 
 _SIGNATURES = {
@@ -49,6 +57,7 @@ _SIGNATURES = {
     'ddg_groupnorm_bwd': ([_P] * 9 + [_I] * 6 + [_P], _I),
     'ddg_timestep_embedding': ([_P, _P, _I, _I, _F, _P], _I),
     'ddg_linear': ([_P] * 4 + [_I] * 8 + [_P], _I),
+    'ddg_mlp_rows': ([_P, _I, _P, _I, _I, _P, _P], _I),
     'ddg_q_sample_pairs': ([_P] * 10 + [_I, _L, _P], _I),
     'ddg_sample_posterior': ([_P] * 8 + [_I, _L, _P], _I),
     'ddg_nchw_to_pnhwc': ([_P, _I, _P, _I, _P, _I, _I, _I, _I, _F, _F, _P], _I),

@@ -200,25 +200,21 @@ class GeneratorEngine(_EngineBase):
         used_holder = [0]
         self._step(lambda: self._stats_arena[:used_holder[0]].zero_())
         # z mapping (ncsnpp_generator_adagn.py:51-56, 271-277) and time embedding (:295-303)
-        zb = [torch.empty(N, zd, device=dev) for _ in range(2)]
-        # activations are applied as the prologue of the consuming GEMM, so every layer after the first (K = nz is not a
-        # multiple of the K block) runs on the tensor-core GEMM path
-        self._step(lambda: ops.linear(self.z_in, P['z_transform.1.weight'], P['z_transform.1.bias'], pixel_norm=True, out=zb[0]))
-        cur = 0
-        for i in range(cfg.n_mlp):
-            nme = f'z_transform.{3 + 2 * i}'
-            self._linear_rows(zb[cur], zd, P[nme + '.weight'], P[nme + '.bias'], zb[1 - cur], act_in=ops.ACT_SILU)
-            cur = 1 - cur
-        self.zemb_pre = zb[cur]                          # pre-activation; SiLU is folded into the style GEMM's prologue
+        # z-mapping network and time-embedding MLP: one kernel each (ddg_mlp_rows); their last activation is applied as the
+        # prologue of the consuming GEMM (style / Dense_0 projections)
+        znames = ['z_transform.1'] + [f'z_transform.{3 + 2 * i}' for i in range(cfg.n_mlp)]
+        zdesc = ops.make_mlp_desc([P[k + '.weight'] for k in znames], [P[k + '.bias'] for k in znames], act=ops.ACT_SILU, pixel_norm=True)
+        self.zemb_pre = torch.empty(N, zd, device=dev)
+        self._step(lambda: ops.mlp_rows(self.z_in, zdesc, self.zemb_pre))
         temb0 = torch.empty(N, nf, device=dev)
-        temb1 = torch.empty(N, 4 * nf, device=dev)
         self.temb = torch.empty(N, 4 * nf, device=dev)
+        tdesc = ops.make_mlp_desc([P['all_modules.0.weight'], P['all_modules.1.weight']], [P['all_modules.0.bias'], P['all_modules.1.bias']],
+                                  act=ops.ACT_SILU)
         self._step(lambda: ops.timestep_embedding(self.t_in, nf, out=temb0))
-        self._linear_rows(temb0, nf, P['all_modules.0.weight'], P['all_modules.0.bias'], temb1)
-        self._linear_rows(temb1, 4 * nf, P['all_modules.1.weight'], P['all_modules.1.bias'], self.temb, act_in=ops.ACT_SILU)
+        self._step(lambda: ops.mlp_rows(temb0, tdesc, self.temb))
         self._linear_rows(self.zemb_pre, zd, self._w_style, self._b_style, self.style_all, act_in=ops.ACT_SILU)
         self._linear_rows(self.temb, 4 * nf, self._w_dense, self._b_dense, self.dense_all, act_in=ops.ACT_SILU)
-        self._keep.append((zb, temb0, temb1))
+        self._keep.append((zdesc, tdesc, temb0))
 
         # input image -> PNHWC (channels padded to 32); "2x-1" when data is not centered (:308-310)
         cp_in = ops.pad_c(cfg.num_channels)

@@ -126,6 +126,29 @@ def linear(x, W, b=None, act_in=ACT_NONE, act_out=ACT_NONE, pixel_norm=False, ou
     return out
 
 
+def make_mlp_desc(weights, biases, act=ACT_SILU, pixel_norm=False):
+    """Descriptor of ddg_mlp_rows for nn.Linear-layout layers (W_i [out, in]); keeps no reference to the tensors."""
+    d = _lib.MlpDesc()
+    assert 1 <= len(weights) <= _lib.MLP_MAX_LAYERS
+    for i, (w, b) in enumerate(zip(weights, biases)):
+        require_cuda_f32(w, b)
+        assert w.is_contiguous() and (b is None or b.is_contiguous())
+        d.W[i] = w.data_ptr(); d.b[i] = b.data_ptr() if b is not None else None
+        d.dims[i] = w.shape[1]; d.dims[i + 1] = w.shape[0]
+        if i > 0:
+            assert weights[i - 1].shape[0] == w.shape[1], 'layer widths do not chain'
+    d.nlayers = len(weights); d.pixel_norm = int(pixel_norm); d.act = act
+    return d
+
+
+def mlp_rows(x, desc, out):
+    """out[N, J] = the whole MLP described by `desc` applied to the rows of x (one kernel launch)."""
+    require_cuda_f32(x, out)
+    assert x.stride(1) == 1 and out.stride(1) == 1 and x.shape[1] == desc.dims[0] and out.shape[1] == desc.dims[desc.nlayers]
+    check(lib().ddg_mlp_rows(ptr(x), x.stride(0), ptr(out), out.stride(0), x.shape[0], C.byref(desc), stream()), 'mlp_rows')
+    return out
+
+
 def q_sample_pairs(x0, noise_xt, noise_xtp1, t, a_s_cum, sigmas_cum, a_s, sigmas, out=None):
     require_cuda_f32(x0, noise_xt, noise_xtp1, a_s_cum, sigmas_cum, a_s, sigmas)
     x0, noise_xt, noise_xtp1 = x0.contiguous(), noise_xt.contiguous(), noise_xtp1.contiguous()

@@ -60,6 +60,21 @@ int ddg_timestep_embedding(const int64_t* t, float* out, int N, int dim, float m
  * (:271-277), the temb MLP (:301-303), AdaGN style projections (layerspp.py:57) and Dense_0 (:298-299). */
 int ddg_linear(const float* x, const float* W, const float* b, float* y, int N, int K, int J, int ldx, int ldy, int act_in,
                int act_out, int pixel_norm, cudaStream_t stream);
+/* A whole small MLP on [N, K0] rows as ONE kernel: y = L_{n-1}(act(... act(L_0(norm(x))) ...)), L_i(v) = W_i v + b_i with W_i
+ * [dims[i+1]][dims[i]] (nn.Linear layout).  pixel_norm applies ncsnpp_generator_adagn.py:51-56 to the input row; `act` is
+ * applied between layers (not after the last one: consumers fold it into their prologue).  Replaces the z-mapping network
+ * (PixelNorm + 1 + n_mlp dense layers, ncsnpp_generator_adagn.py:271-277) and the time-embedding MLP (:301-303).
+ * Limits: nlayers <= DDG_MLP_MAX_LAYERS, every dims[i] <= 1024. */
+#define DDG_MLP_MAX_LAYERS 8
+typedef struct {
+  const float* W[DDG_MLP_MAX_LAYERS];
+  const float* b[DDG_MLP_MAX_LAYERS];
+  int dims[DDG_MLP_MAX_LAYERS + 1];
+  int nlayers;
+  int pixel_norm;
+  int act;
+} ddg_mlp_desc;
+int ddg_mlp_rows(const float* x, int ldx, float* y, int ldy, int N, const ddg_mlp_desc* desc, cudaStream_t stream);
 /* ddgan.py:110-126 q_sample_pairs with injected noise: x_t = a_cum[t] x0 + s_cum[t] n0 ; x_tp1 = a[t+1] x_t + s[t+1] n1 */
 int ddg_q_sample_pairs(const float* x0, const float* noise_xt, const float* noise_xtp1, const int64_t* t, const float* a_s_cum,
                        const float* sigmas_cum, const float* a_s, const float* sigmas, float* x_t, float* x_tp1, int N,

@@ -125,6 +125,31 @@ def test_small_kernels(ops):
     assert O.rel_l2(xp.cpu(), O.sample_posterior(pc, x0, n0, t3, n1)) < 1e-6
 
 
+def test_mlp_rows_single_kernel(ops):
+    """z-mapping network (PixelNorm + 5 dense + SiLU between) and a 2-layer time-embedding MLP as one launch each."""
+    n, nz, zd = 13, 100, 256                                   # rows not a multiple of the 8-row CTA, K0 not a multiple of 64
+    z = seeded((n, nz), 70)
+    Ws = [seeded((zd, nz), 71, 0.1)] + [seeded((zd, zd), 72 + i, 0.08) for i in range(4)]
+    bs = [seeded((zd,), 80 + i, 0.1) for i in range(5)]
+    h = z / torch.sqrt(torch.mean(z ** 2, dim=1, keepdim=True) + 1e-8)
+    for i, (w, b) in enumerate(zip(Ws, bs)):
+        h = F.linear(h, w, b)
+        if i < 4:
+            h = F.silu(h)
+    desc = ops.make_mlp_desc([w.to(DEV) for w in Ws], [b.to(DEV) for b in bs], act=ops.ACT_SILU, pixel_norm=True)
+    keep = desc  # noqa: F841 (device tensors above stay alive through the local lists below)
+    Wd = [w.to(DEV) for w in Ws]; bd = [b.to(DEV) for b in bs]
+    desc = ops.make_mlp_desc(Wd, bd, act=ops.ACT_SILU, pixel_norm=True)
+    out = ops.mlp_rows(z.to(DEV), desc, torch.empty(n, zd, device=DEV))
+    assert O.rel_l2(out.cpu(), h) < 1e-5
+    # 128 -> 512 -> 512 (temb MLP shape), no normalisation, 64 rows
+    t0 = seeded((64, 128), 90); W0 = seeded((512, 128), 91, 0.1).to(DEV); W1 = seeded((512, 512), 92, 0.05).to(DEV)
+    b0 = seeded((512,), 93, 0.1).to(DEV); b1 = seeded((512,), 94, 0.1).to(DEV)
+    ref = F.linear(F.silu(F.linear(t0, W0.cpu(), b0.cpu())), W1.cpu(), b1.cpu())
+    out = ops.mlp_rows(t0.to(DEV), ops.make_mlp_desc([W0, W1], [b0, b1]), torch.empty(64, 512, device=DEV))
+    assert O.rel_l2(out.cpu(), ref) < 1e-5
+
+
 def test_layout_roundtrip_and_fir(ops):
     a = seeded((3, 3, 8, 8), 22); b = seeded((3, 3, 8, 8), 23)
     p = ops.to_pnhwc(a.to(DEV), b.to(DEV), cpad=32)
