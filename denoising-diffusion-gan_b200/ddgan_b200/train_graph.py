@@ -197,8 +197,25 @@ class WgradFn(Function):
         return g_x, g_dy, None
 
 
+def _pad_cout(w, b, out_nchw=False):
+    """PNHWC outputs carry pad_c(Cout) channels and the kernel writes whole 32-channel chunks: give odd Cout zero weight rows
+    (differentiable: the gradient of F.pad slices them off again)."""
+    cout = w.shape[0]
+    cp = ops.pad_c(cout)
+    if out_nchw or cp == cout:
+        return w, b
+    w = F.pad(w, (0, 0) * (w.dim() - 1) + (0, cp - cout))
+    if b is not None:
+        b = F.pad(b, (0, cp - cout))
+    return w, b
+
+
 def conv3x3(x, w, b, n, h, wd, addvec=None, out_nchw=False, prec=3, res=None, out_scale=1.0):
     """nn.Conv2d(k=3, s=1, p=1) on PNHWC; w [Cout, Cin, 3, 3] (zero-padded along Cin to x's channel count if needed)."""
+    cout_real = w.shape[0]
+    w, b = _pad_cout(w, b, out_nchw)
+    if addvec is not None and w.shape[0] != cout_real:
+        addvec = F.pad(addvec, (0, w.shape[0] - cout_real))
     cout, cin = w.shape[0], w.shape[1]
     cp = x.shape[-1]
     if cin < cp:
@@ -209,6 +226,7 @@ def conv3x3(x, w, b, n, h, wd, addvec=None, out_nchw=False, prec=3, res=None, ou
 
 def conv1x1(x, w, b, n, h, wd, prec=3, res=None, out_scale=1.0):
     """1x1 conv; w [Cout, Cin, 1, 1] or [Cout, Cin]."""
+    w, b = _pad_cout(w, b)
     cout, cin = w.shape[0], w.shape[1]
     cp = x.shape[-1]
     w2 = w.reshape(cout, cin)
@@ -374,6 +392,29 @@ def _interior(x):
     return x[:, 1:-1, 1:-1, :]
 
 
+def conv_downsample_pnhwc(x, wt, bias, n, h, w, prec=3, res=None, out_scale=1.0):
+    """up_or_down_sampling.py:226-262 conv_downsample_2d with k = [1,3,3,1], factor 2 on a PNHWC tensor: pad(2,2) FIR written
+    space-to-depth (FirFn mode 3), then the stride-2 3x3 conv as a stride-1 2x2-tap conv over the 4*C s2d channels.
+    x [N, h+2, w+2, cp]; wt [Cout, Cin, 3, 3]; returns PNHWC [N, h/2+2, w/2+2, pad_c(Cout)] = out_scale * (conv + bias + res)."""
+    cp = x.shape[-1]
+    ho, wo = h // 2, w // 2
+    s2d = FirFn.apply(x, 3, 1.0, 0)                           # [N, ho+3, wo+3, 4*cp]
+    wt, bias = _pad_cout(wt, bias)
+    cout, cin = wt.shape[0], wt.shape[1]
+    w2 = wt.new_zeros(cout, 2, 2, cp, 2, 2)
+    for dy in range(2):
+        for dx in range(2):
+            for py in range(2):
+                for px in range(2):
+                    r, s_ = 2 * dy + py, 2 * dx + px
+                    if r < 3 and s_ < 3:
+                        w2[:, py, px, :cin, dy, dx] = wt[:, :, r, s_]
+    w2 = w2.reshape(cout, 4 * cp, 4)
+    sp = conv_spec(w2.shape, ops.TAPS_2X2, n, ho, wo, 4 * cp, 4 * cp * 4, 4, 1, cout, 4 * cp, hp=ho + 3, wp=wo + 3, prec=prec,
+                   out_scale=out_scale)
+    return ConvFn.apply(s2d, w2, bias, None, res, sp)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # generator
 # ------------------------------------------------------------------------------------------------------------------
@@ -455,23 +496,8 @@ def generator_forward(mod, x, time_cond, z):
     def pyramid_down(m, pyr, hcur, h, w):
         """conv_downsample_2d + bias, then (pyramid + h)/sqrt2 (ncsnpp...:343-350); h, w = input size of pyr."""
         pn = f"all_modules.{m['idx']}.Conv2d_0"
-        cp = pyr.shape[-1]
-        ho, wo = h // 2, w // 2
-        s2d = FirFn.apply(pyr, 3, 1.0, 0)                       # [N, ho+3, wo+3, 4*cp]
-        wt = P[pn + '.weight']
-        cout, cin = wt.shape[0], wt.shape[1]
-        w2 = wt.new_zeros(cout, 2, 2, cp, 2, 2)
-        for dy in range(2):
-            for dx in range(2):
-                for py in range(2):
-                    for px in range(2):
-                        r, s_ = 2 * dy + py, 2 * dx + px
-                        if r < 3 and s_ < 3:
-                            w2[:, py, px, :cin, dy, dx] = wt[:, :, r, s_]
-        w2 = w2.reshape(cout, 4 * cp, 4)
-        sp = conv_spec(w2.shape, ops.TAPS_2X2, N, ho, wo, 4 * cp, 4 * cp * 4, 4, 1, cout, 4 * cp, hp=ho + 3, wp=wo + 3, prec=prec,
-                       out_scale=RSQRT2 if cfg.skip_rescale else 1.0)
-        return ConvFn.apply(s2d, w2, P[pn + '.bias'], None, hcur, sp)
+        return conv_downsample_pnhwc(pyr, P[pn + '.weight'], P[pn + '.bias'], N, h, w, prec=prec, res=hcur,
+                                     out_scale=RSQRT2 if cfg.skip_rescale else 1.0)
 
     mods = arch.ncsnpp_modules(cfg)
     xin = x if cfg.centered else 2 * x - 1.0

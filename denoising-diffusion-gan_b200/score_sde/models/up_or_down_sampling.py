@@ -31,13 +31,23 @@ def downsample_2d(x, k=None, factor=2, gain=1):
 
 
 def conv_downsample_2d(x, w, k=None, factor=2, gain=1):
+    """FIR (pad = (p+1)//2, p//2 with p = (len(k) - factor) + (convW - 1)) followed by the stride-`factor` convolution, both on
+    this library's kernels: the FIR output is written space-to-depth and the strided 3x3 conv runs as a stride-1 2x2-tap
+    tensor-core conv (ddgan_b200.train_graph.conv_downsample_pnhwc).  Supported: the configuration the reference uses,
+    k = [1, 3, 3, 1], factor 2, 3x3 weights, even H and W (up_or_down_sampling.py:75-79)."""
     assert isinstance(factor, int) and factor >= 1
     _outC, _inC, convH, convW = w.shape
     assert convW == convH
-    k = _setup_kernel([1] * factor if k is None else k) * gain
-    p = (k.shape[0] - factor) + (convW - 1)
-    x = upfirdn2d(x, torch.tensor(k, device=x.device), pad=((p + 1) // 2, p // 2))
-    return F.conv2d(x, w, stride=factor, padding=0)
+    kk = _setup_kernel([1] * factor if k is None else k) * gain
+    ref = _setup_kernel([1, 3, 3, 1])
+    if factor != 2 or convW != 3 or kk.shape != ref.shape or not np.allclose(kk, ref) or x.shape[2] % 2 or x.shape[3] % 2:
+        raise NotImplementedError('conv_downsample_2d: only k=[1,3,3,1], factor=2, 3x3 weights, even sizes (the reference configuration)')
+    from ddgan_b200 import train_graph as TG, ops
+    n, c, h, wd = x.shape
+    xp = TG.ToPnhwcFn.apply(x, ops.pad_c(c))
+    y = TG.conv_downsample_pnhwc(xp, w, None, n, h, wd)
+    return TG.FromPnhwcFn.apply(y, _outC)
+
 
 
 def naive_upsample_2d(x, factor=2):
