@@ -94,6 +94,7 @@ struct WgradDev {
   int splits_pad;      // split slots per (co, ci, tap-group) block, a multiple of the cluster size; blockIdx.z = grp * splits_pad + split
   int cs;              // cluster size along z: the CTAs of one cluster hold partial sums of the same dW block
   float gain;          // multiplies the block before it is added to dW
+  long long* prof;     // optional per-role cycle counters of one CTA
   int order;           // dW walk of the final reduction: 0 = taps fastest, then ci, then co (conv layouts); 1 = co fastest (NIN [in][out])
 };
 
@@ -158,11 +159,71 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const __grid_con
       *reinterpret_cast<uint4*>(dst_hi) = hi;
       if (NPL == 2) *reinterpret_cast<uint4*>(dst_lo) = lo;
     };
+    const bool prof_on = p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == gridDim.z / 2;
+    long long w_empty = 0;
+    const long long t_p0 = clock64();
+    // Batched path (NCI = 128: 4 dY items + <= 5 X items of 32 bytes per thread and tile): every load of a tile is issued before
+    // the first conversion, so the L2 / HBM latency is exposed once per tile instead of three times (dY batch, X batch, X tail:
+    // ncu attributes a third of the stall samples to the first use of loaded data; the producer ran at 3.9 K cycles per tile
+    // against 2.3 K of MMA work).
+    constexpr int UDY = (KT * DY_CH) / NPT;          // 4 for KT = 64
+    constexpr int UXM = 5;
+    const bool batched = (NCI == 128) && ((KT * DY_CH) % NPT == 0) && (xrows * X_CH <= UXM * NPT);
+    if (batched) {
+      const int nx = xrows * X_CH;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int st = it % NST;
+        const uint32_t ph = (it / NST) & 1;
+        const int q0 = (tile0 + it) * KT;
+        float4 a[UDY + UXM], b[UDY + UXM];
+#pragma unroll
+        for (int u = 0; u < UDY; ++u) {
+          const int item = tid + u * NPT;
+          const int c = item % DY_CH, e = item / DY_CH;
+          const int q = q0 + e;
+          a[u] = b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (q < p.Mtotal && co0 + c * 8 < p.dy_c) {
+            const float4* src = reinterpret_cast<const float4*>(p.dy + (size_t)q * p.dypitch + co0 + c * 8);
+            a[u] = __ldg(src); b[u] = __ldg(src + 1);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UXM; ++u) {
+          const int item = tid + u * NPT;
+          const int c = item % X_CH, e = item / X_CH;
+          const int g = q0 + minoff + e;
+          a[UDY + u] = b[UDY + u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (item < nx && g >= 0 && g < p.Mtotal) {
+            const float4* src = reinterpret_cast<const float4*>(p.x + (size_t)g * p.xpitch + ci0 + c * 8);
+            a[UDY + u] = __ldg(src); b[UDY + u] = __ldg(src + 1);
+          }
+        }
+        { const long long tw = clock64(); w_mbar_wait(empty(st), ph ^ 1); w_empty += clock64() - tw; }
+        uint8_t* sdy = sbase + st * stage_bytes;
+        uint8_t* sx = sdy + NPL * DY_PLANE;
+#pragma unroll
+        for (int u = 0; u < UDY; ++u) {
+          const int item = tid + u * NPT;
+          const int c = item % DY_CH, e = item / DY_CH;
+          cvt_store(a[u], b[u], sdy + c * DY_PITCH + e * 16, sdy + DY_PLANE + c * DY_PITCH + e * 16);
+        }
+#pragma unroll
+        for (int u = 0; u < UXM; ++u) {
+          const int item = tid + u * NPT;
+          if (item < nx) {
+            const int c = item % X_CH, e = item / X_CH;
+            cvt_store(a[UDY + u], b[UDY + u], sx + c * p.xpitch_b + e * 16, sx + x_plane + c * p.xpitch_b + e * 16);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        w_mbar_arrive(full(st));
+      }
+    } else
     for (int it = 0; it < my_tiles; ++it) {
       const int st = it % NST;
       const uint32_t ph = (it / NST) & 1;
       const int q0 = (tile0 + it) * KT;
-      w_mbar_wait(empty(st), ph ^ 1);
+      { const long long tw = clock64(); w_mbar_wait(empty(st), ph ^ 1); w_empty += clock64() - tw; }
       uint8_t* sdy = sbase + st * stage_bytes;
       uint8_t* sx = sdy + NPL * DY_PLANE;
       // dY tile: KT rows x 16 chunks
@@ -218,7 +279,9 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const __grid_con
     // ============================ epilogue 1/2: TMEM -> shared-memory staging in dW walk order ============================
     // (the operand ring is dead once accFull fires).  Row pitches are chosen so that the 32 lanes (= 32 output channels) of one
     // store hit 32 banks; split slots past the last pixel tile stage zeros.
+    const long long t_p1 = clock64();
     w_mbar_wait(accFull, 0);
+    const long long t_p2 = clock64();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     {
       float* S = reinterpret_cast<float*>(sbase);
@@ -248,6 +311,13 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const __grid_con
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (prof_on && tid == 0) {
+      p.prof[0] = t_p1 - t_p0;            // producer loop
+      p.prof[1] = w_empty;                // ... waiting for a free stage
+      p.prof[2] = t_p2 - t_p1;            // waiting for the last MMAs
+      p.prof[3] = clock64() - t_p2;       // TMEM -> smem staging
+      p.prof[4] = my_tiles;
+    }
   } else {
     // ============================ MMA issuer ============================
     // converged warp, one elected lane issues; descriptors advance with one 32-bit add (see conv_tc.cu)
@@ -260,9 +330,11 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const __grid_con
       const uint32_t lbo_f = ((128u >> 4) & 0x3FFF) << 16;
       const uint32_t a_hi32 = (((uint32_t)DY_PITCH >> 4) & 0x3FFF) | (1u << 14);
       const uint32_t b_hi32 = (((uint32_t)p.xpitch_b >> 4) & 0x3FFF) | (1u << 14);
+      long long w_full = 0;
+      const long long t_m0 = clock64();
       for (int it = 0; it < my_tiles; ++it) {
         const int st = it % NST;
-        w_mbar_wait(full(st), (it / NST) & 1);
+        { const long long tw = clock64(); w_mbar_wait(full(st), (it / NST) & 1); w_full += clock64() - tw; }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (leader) {
           const uint32_t dy_hi = lbo_f | ((w_smem_u32(sbase + st * stage_bytes) >> 4) & 0x3FFFu);   // CTA-local offset: in a cluster the window base is rank << 24
@@ -297,6 +369,10 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_tc_kernel(const __grid_con
         __syncwarp();
       }
       if (leader) w_commit(accFull);
+      if (leader && p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == gridDim.z / 2) {
+        p.prof[5] = clock64() - t_m0;       // MMA issue loop
+        p.prof[6] = w_full;                 // ... waiting for operands
+      }
       __syncwarp();
     }
   }
@@ -470,6 +546,7 @@ extern "C" int ddg_conv2d_wgrad(const ddg_wgrad_desc* c, cudaStream_t stream) {
   for (int t = 0; t < c->ntaps; ++t) d.tapoff[t] = c->tap_dr[t] * c->Wp + c->tap_ds[t];
   d.s_co = c->s_co; d.s_ci = c->s_ci; d.s_tap = c->s_tap;
   d.gain = c->gain == 0.f ? 1.f : c->gain;
+  d.prof = (long long*)c->debug_prof;
   const int prec = c->precision == 1 ? 1 : 3;
   if (c->Cin_pad % 128 == 0) {
     // one tap row per CTA: 3x3 -> 3 groups of 3, 2x2 -> 2 groups of 2, 1x1 -> 1 group

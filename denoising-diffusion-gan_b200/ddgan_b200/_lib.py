@@ -34,7 +34,7 @@ class WgradDesc(C.Structure):
     _fields_ = [('x', C.c_void_p), ('dy', C.c_void_p), ('dw', C.c_void_p), ('xpitch', C.c_int), ('dypitch', C.c_int),
                 ('N', C.c_int), ('Hp', C.c_int), ('Wp', C.c_int), ('Cout', C.c_int), ('dy_cpad', C.c_int),
                 ('Cin_real', C.c_int), ('Cin_pad', C.c_int), ('ntaps', C.c_int), ('tap_dr', C.c_int8 * 9),
-                ('tap_ds', C.c_int8 * 9), ('s_co', C.c_long), ('s_ci', C.c_long), ('s_tap', C.c_long), ('precision', C.c_int), ('gain', C.c_float)]
+                ('tap_ds', C.c_int8 * 9), ('s_co', C.c_long), ('s_ci', C.c_long), ('s_tap', C.c_long), ('precision', C.c_int), ('gain', C.c_float), ('debug_prof', C.c_void_p)]
 
 
 MLP_MAX_LAYERS = 8

@@ -282,7 +282,7 @@ def stats_bwd(x, g):
 
 
 def conv_wgrad(x, dy, dw, n, hp, wp, cout, cin_real, cin_pad, taps, s_co, s_ci, s_tap, precision=3, xpitch=None, dypitch=None,
-               dy_cpad=None, x_elem_offset=0, flops=None, gain=1.0):
+               dy_cpad=None, x_elem_offset=0, flops=None, gain=1.0, prof=None):
     """dw[co*s_co + ci*s_ci + t*s_tap] += sum_q dy[q][co] * x[q + tap_t][ci]  (dw zero-initialised by the caller)."""
     d = _lib.WgradDesc()
     d.x = x.data_ptr() + 4 * x_elem_offset; d.dy = ptr(dy); d.dw = ptr(dw)
@@ -295,6 +295,7 @@ def conv_wgrad(x, dy, dw, n, hp, wp, cout, cin_real, cin_pad, taps, s_co, s_ci, 
     d.s_co, d.s_ci, d.s_tap = s_co, s_ci, s_tap
     d.precision = precision
     d.gain = gain
+    d.debug_prof = prof.data_ptr() if prof is not None else None
     if PROFILE['on']:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()

@@ -190,6 +190,7 @@ typedef struct {
   long s_co, s_ci, s_tap;
   int precision;
   float gain;                  /* dw += gain * (...); 0 is read as 1 (the adjoint of a conv whose epilogue applies out_scale) */
+  void* debug_prof;            /* optional int64[8] device buffer: per-role cycle counters of one CTA (tuning aid), or NULL */
 } ddg_wgrad_desc;
 int ddg_conv2d_wgrad(const ddg_wgrad_desc* desc, cudaStream_t stream);
 
