@@ -357,29 +357,41 @@ def _tc_linear(n, k, j):
 
 
 class LinearFn(Function):
-    """y = x W^T + b on [N, K] rows (forward and both gradient GEMMs): ddg_linear, or the tensor-core GEMMs for wide layers."""
+    """y = x W^T + b on [N, K] rows (forward and both gradient GEMMs): ddg_linear, or the tensor-core GEMMs for wide layers.
+    Closed under differentiation: under create_graph the backward is expressed with LinearFn itself (dx = dy W is a linear
+    layer with weight W^T, dW = dy^T x one with weight x^T), which the R1 penalty needs through the discriminator's
+    end_linear (discriminator.py:165-167)."""
 
     @staticmethod
     def forward(ctx, x, W, b):
-        x, W = x.contiguous(), W.contiguous()
         ctx.save_for_backward(x, W)
         ctx.has_b = b is not None
-        if _tc_linear(x.shape[0], x.shape[1], W.shape[0]):
-            return ops.gemm_rows(x, W, b)
-        return ops.linear(x, W, b)
+        xc, Wc = x.contiguous(), W.contiguous()
+        if _tc_linear(xc.shape[0], xc.shape[1], Wc.shape[0]):
+            return ops.gemm_rows(xc, Wc, b)
+        return ops.linear(xc, Wc, b)
 
     @staticmethod
     def backward(ctx, dy):
         x, W = ctx.saved_tensors
-        dy = dy.contiguous()
-        tc = _tc_linear(x.shape[0], x.shape[1], W.shape[0])
         dx = dW = None
+        if torch.is_grad_enabled():
+            # differentiable backward (double backward of the gradient penalty)
+            if ctx.needs_input_grad[0]:
+                dx = LinearFn.apply(dy, W.t(), None)
+            if ctx.needs_input_grad[1]:
+                dW = LinearFn.apply(dy.t(), x.t(), None)
+            db = dy.sum(0) if (ctx.has_b and ctx.needs_input_grad[2]) else None
+            return dx, dW, db
+        dy = dy.contiguous()
+        xc, Wc = x.contiguous(), W.contiguous()
+        tc = _tc_linear(xc.shape[0], xc.shape[1], Wc.shape[0])
         if ctx.needs_input_grad[0]:
             # dx[n][k] = sum_j dy[n][j] W[j][k]: contraction over the J rows of dy^T and W
-            dx = ops.gemm_tn(dy.t().contiguous(), W) if tc else ops.linear(dy, W.t().contiguous())
+            dx = ops.gemm_tn(dy.t().contiguous(), Wc) if tc else ops.linear(dy, Wc.t().contiguous())
         if ctx.needs_input_grad[1]:
             # dW[j][k] = sum_n dy[n][j] x[n][k]: contraction over the batch rows
-            dW = ops.gemm_tn(dy, x) if tc else ops.linear(dy.t().contiguous(), x.t().contiguous())
+            dW = ops.gemm_tn(dy, xc) if tc else ops.linear(dy.t().contiguous(), xc.t().contiguous())
         db = dy.sum(0) if (ctx.has_b and ctx.needs_input_grad[2]) else None
         return dx, dW, db
 
@@ -555,15 +567,15 @@ def discriminator_forward(mod, x, t, x_t):
     prec = mod.precision
     N, S = x.shape[0], x.shape[-1]
     te = ops.timestep_embedding(t, mod.t_emb_dim)
-    te = F.linear(te, P['t_embed.main.0.weight'], P['t_embed.main.0.bias'])
-    te = F.linear(F.leaky_relu(te, 0.2), P['t_embed.main.2.weight'], P['t_embed.main.2.bias'])
+    te = LinearFn.apply(te, P['t_embed.main.0.weight'], P['t_embed.main.0.bias'])
+    te = LinearFn.apply(F.leaky_relu(te, 0.2), P['t_embed.main.2.weight'], P['t_embed.main.2.bias'])
     te = F.leaky_relu(te, 0.2)
     xin = ToPnhwcFn.apply(torch.cat((x, x_t), dim=1), ops.pad_c(mod.nc))
     h = conv1x1(xin, P['start_conv.weight'], P['start_conv.bias'], N, S, S, prec=prec)
     cur = S
     for i, (a, b, ds) in enumerate(arch.discriminator_blocks(mod.ngf, mod.large)):
         pn = f'conv{i + 1}.'
-        dense = F.linear(te, P[pn + 'dense_t1.weight'], P[pn + 'dense_t1.bias'])
+        dense = LinearFn.apply(te, P[pn + 'dense_t1.weight'], P[pn + 'dense_t1.bias'])
         o = conv3x3(F.leaky_relu(h, 0.2), P[pn + 'conv1.0.weight'], P[pn + 'conv1.0.bias'], N, cur, cur, addvec=dense, prec=prec)
         o = F.leaky_relu(o, 0.2)
         xs = h
@@ -584,4 +596,4 @@ def discriminator_forward(mod, x, t, x_t):
     hcat = torch.cat([h, extra], dim=-1)
     f = conv3x3(hcat, P['final_conv.weight'], P['final_conv.bias'], N, cur, cur, prec=prec)
     f = F.leaky_relu(_interior(f), 0.2).sum(dim=(1, 2))            # [N, C]
-    return F.linear(f, P['end_linear.weight'], P['end_linear.bias'])
+    return LinearFn.apply(f, P['end_linear.weight'], P['end_linear.bias'])
