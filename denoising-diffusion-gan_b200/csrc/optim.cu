@@ -48,12 +48,14 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 __global__ void __launch_bounds__(256) adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                       float* __restrict__ v, float* __restrict__ ema, long n,
                                                       const float* __restrict__ state, const double* __restrict__ normsq, float max_norm,
-                                                      float b1, float b2, float eps, float wd, float ema_decay) {
+                                                      float b1, float b2, float eps, float wd, float ema_decay, float grad_scale) {
   const float step = state[0], lr = state[1];
-  float clip = 1.f;
+  // grad_scale (1/world after a sum all-reduce) is applied to the gradient before everything else: the norm of the scaled
+  // gradient is grad_scale * sqrt(normsq), and the clip factor multiplies on top of it
+  float clip = grad_scale;
   if (normsq != nullptr && max_norm > 0.f) {
-    const float total = (float)sqrt(*normsq);
-    clip = fminf(max_norm / (total + 1e-6f), 1.f);   // torch.nn.utils.clip_grad_norm_
+    const float total = (float)sqrt(*normsq) * grad_scale;
+    clip = grad_scale * fminf(max_norm / (total + 1e-6f), 1.f);   // torch.nn.utils.clip_grad_norm_
   }
   const float bc1 = 1.f - powf(b1, step);
   const float bc2_sqrt = sqrtf(1.f - powf(b2, step));
@@ -99,7 +101,7 @@ extern "C" int ddg_grad_norm_sq(const float* g, long n, double* out, cudaStream_
 
 extern "C" int ddg_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, long n, float* state, const double* normsq,
                                  float max_norm, float beta1, float beta2, float eps, float weight_decay, float ema_decay,
-                                 cudaStream_t stream) {
+                                 float grad_scale, cudaStream_t stream) {
   if (!p || !g || !m || !v || !state || n < 0) { ddg_set_last_error("adam_ema_step: bad args"); return DDG_ERR_ARG; }
   if (((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v) | ((uintptr_t)(ema ? ema : p))) & 15) != 0) {
     ddg_set_last_error("adam_ema_step: arenas must be 16-byte aligned");
@@ -109,7 +111,7 @@ extern "C" int ddg_adam_ema_step(float* p, const float* g, float* m, float* v, f
   long blocks = (n / 4 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  adam_ema_kernel<<<(int)blocks, 256, 0, stream>>>(p, g, m, v, ema, n, state, normsq, max_norm, beta1, beta2, eps, weight_decay, ema_decay);
+  adam_ema_kernel<<<(int)blocks, 256, 0, stream>>>(p, g, m, v, ema, n, state, normsq, max_norm, beta1, beta2, eps, weight_decay, ema_decay, grad_scale);
   DDG_CHECK_LAUNCH();
   return DDG_OK;
 }

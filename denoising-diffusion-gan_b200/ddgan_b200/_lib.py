@@ -81,7 +81,7 @@ _SIGNATURES = {
     'ddg_stats_fwd': ([_P, _P, _I, _I, _I, _I, _P], _I),
     'ddg_stats_bwd': ([_P, _P, _P, _I, _I, _I, _I, _P], _I),
     'ddg_grad_norm_sq': ([_P, _L, _P, _P], _I),
-    'ddg_adam_ema_step': ([_P, _P, _P, _P, _P, _L, _P, _P, _F, _F, _F, _F, _F, _F, _P], _I),
+    'ddg_adam_ema_step': ([_P, _P, _P, _P, _P, _L, _P, _P, _F, _F, _F, _F, _F, _F, _F, _P], _I),
 }
 
 _lib = None

@@ -441,7 +441,10 @@ class DiscriminatorEngine(_EngineBase):
     def __init__(self, nc, ngf, t_emb_dim, image_size, batch, large=False, device='cuda', precision=3):
         super().__init__(batch, device, precision, arch.discriminator_param_shapes(nc, ngf, t_emb_dim, large))
         self.nc, self.ngf, self.t_emb_dim, self.S, self.large = nc, ngf, t_emb_dim, image_size, large
-        assert nc % 2 == 0 and (2 * ngf) % 32 == 0
+        # narrow maps (2*ngf, 4*ngf not multiples of 32) live in buffers padded to 32 channels whose extra channels stay zero;
+        # the minibatch-stddev / final_conv stage needs its 8*ngf channels unpadded
+        if nc % 2 != 0 or (8 * ngf) % 32 != 0:
+            raise NotImplementedError('DiscriminatorEngine needs an even nc and ngf % 4 == 0')
         self._build()
 
     def _build(self):
@@ -478,11 +481,14 @@ class DiscriminatorEngine(_EngineBase):
         xin = Act(self, cp_in, S, S, stats=False)
         self._step(lambda: ops.to_pnhwc(self.x_in, self.xt_in, cpad=cp_in, out=xin.buf))
         c0 = 2 * self.ngf
-        h = Act(self, c0, S, S, stats=False)
+        h = Act(self, ops.pad_c(c0), S, S, stats=False)
         self._conv(c0, [ops.conv_src(xin.buf, cp_in, ops.TAPS_1X1)], S, S, h.buf,
-                   lambda cw: cw.pack_segment(0, P['start_conv.weight'], self.nc, self.nc, 1, 0), bias=P['start_conv.bias'])
+                   lambda cw: cw.pack_segment(0, P['start_conv.weight'], self.nc, self.nc, 1, 0), bias=P['start_conv.bias'],
+                   out_c=h.C)
+        self.stage_acts = [h]                     # start_conv and block outputs (PNHWC), for per-stage parity checks
         for i, (a, b, ds) in enumerate(blocks):
             h = self._down_block(i, h, a, b, ds, offs[i])
+            self.stage_acts.append(h)
         # minibatch stddev (:150-158) as a 1-real-channel PNHWC tensor, then final conv over 512 + 1 channels
         C, H, W = h.C, h.H, h.W
         group = min(N, 4)
@@ -498,35 +504,39 @@ class DiscriminatorEngine(_EngineBase):
         self._conv(C, [ops.conv_src(h.buf, C, ops.TAPS_3X3), ops.conv_src(sdv.buf, 32, ops.TAPS_3X3)], H, W, f.buf, bind_final,
                    bias=P['final_conv.bias'])
         pooled = torch.empty(N, C, device=dev)
+        self.final_feat, self.pooled = f, pooled   # final_conv output before the activation; pooled = sum(leaky(f))
         self._step(lambda i=f.buf: ops.spatial_sum(i, ops.ACT_LEAKY, out=pooled))
         self._step(lambda: ops.linear(pooled, P['end_linear.weight'], P['end_linear.bias'], out=self.out))
         self._keep.append((pooled,))
 
     def _down_block(self, i, X, cin, cout, ds, doff):
-        """DownConvBlock.forward (discriminator.py:76-94)."""
+        """DownConvBlock.forward (discriminator.py:76-94).  cin / cout are the real channel counts; buffers carry pad_c() channels
+        (zero beyond the real ones, zero weight columns for them)."""
         P = self.P
         Pn = f'conv{i + 1}.'
         H, W = X.H, X.W
-        h1 = Act(self, cout, H, W, stats=False)
-        self._conv(cout, [ops.conv_src(X.buf, cin, ops.TAPS_3X3, act=ops.ACT_LEAKY)], H, W, h1.buf,
+        cip, cop = ops.pad_c(cin), ops.pad_c(cout)
+        assert X.C == cip
+        h1 = Act(self, cop, H, W, stats=False)
+        self._conv(cout, [ops.conv_src(X.buf, cip, ops.TAPS_3X3, act=ops.ACT_LEAKY)], H, W, h1.buf,
                    lambda cw: cw.pack_conv_weight(0, P[Pn + 'conv1.0.weight']), bias=P[Pn + 'conv1.0.bias'],
-                   addvec=self.dense_all.data_ptr() + 4 * doff, addvec_stride=self.jd)
+                   addvec=self.dense_all.data_ptr() + 4 * doff, addvec_stride=self.jd, out_c=cop)
         if ds:
             H2, W2 = H // 2, W // 2
-            hf = Act(self, cout, H2, W2, stats=False)
-            xf = Act(self, cin, H2, W2, stats=False)
+            hf = Act(self, cop, H2, W2, stats=False)
+            xf = Act(self, cip, H2, W2, stats=False)
             self._step(lambda i=h1.buf, o=hf.buf: ops.fir_pnhwc(i, 2, o, None, None, ops.ACT_LEAKY))
             self._step(lambda i=X.buf, o=xf.buf: ops.fir_pnhwc(i, 2, o))
-            srcs = [ops.conv_src(hf.buf, cout, ops.TAPS_3X3), ops.conv_src(xf.buf, cin, ops.TAPS_1X1)]
+            srcs = [ops.conv_src(hf.buf, cop, ops.TAPS_3X3), ops.conv_src(xf.buf, cip, ops.TAPS_1X1)]
             H, W = H2, W2
         else:
-            srcs = [ops.conv_src(h1.buf, cout, ops.TAPS_3X3, act=ops.ACT_LEAKY), ops.conv_src(X.buf, cin, ops.TAPS_1X1)]
-        out = Act(self, cout, H, W, stats=False)
+            srcs = [ops.conv_src(h1.buf, cop, ops.TAPS_3X3, act=ops.ACT_LEAKY), ops.conv_src(X.buf, cip, ops.TAPS_1X1)]
+        out = Act(self, cop, H, W, stats=False)
 
         def bind(cw):
             cw.pack_conv_weight(0, P[Pn + 'conv2.0.weight'])
             cw.pack_segment(1, P[Pn + 'skip.0.weight'], cin, cin, 1, 0)
-        self._conv(cout, srcs, H, W, out.buf, bind, bias=P[Pn + 'conv2.0.bias'], out_scale=RSQRT2)
+        self._conv(cout, srcs, H, W, out.buf, bind, bias=P[Pn + 'conv2.0.bias'], out_scale=RSQRT2, out_c=cop)
         return out
 
     def forward(self, x, t, x_t):

@@ -58,32 +58,48 @@ def _dense_layer_init_(t, scale=1.0):
 
 
 class _EngineModule(nn.Module):
-    """Caches one engine per (batch, device) and re-packs its operands when any parameter changed."""
+    """Caches one fused inference engine per (batch, device, precision) and re-packs its operands when the parameters may
+    have changed.
+
+    Staleness rule (no hashing, no collisions):
+      * in train() mode every engine call re-packs -- the weights are being optimised, possibly behind autograd's back
+        (CUDA-graph replays, fused optimisers, `p.data.copy_` as in the reference's ema.py:70-79 / ddgan.py:30-33);
+      * in eval() mode the engine is reused while `(epoch, per-parameter _version, per-parameter data_ptr)` is unchanged;
+        `mark_dirty()` bumps the epoch and must be called by anything that writes parameters without going through a
+        version-counted in-place op (train.FlatAdam, Trainer.step_graphed, train.EMA, train.broadcast_params do)."""
 
     def __init__(self):
         super().__init__()
         self._engines = {}
+        self._epoch = 0
         self.precision = 3  # 3 = BF16x3 (fp32 parity), 1 = BF16
 
-    def _version(self):
-        # _manual_version is bumped by optimisers that update the parameters through raw pointers (train.FlatAdam)
-        return (sum(p._version for p in self.parameters()) + sum(p.data_ptr() % 1009 for p in self.parameters())
-                + 7919 * getattr(self, '_manual_version', 0))
+    def mark_dirty(self):
+        self._epoch += 1
+
+    def _param_key(self):
+        ps = list(self.parameters())
+        return (self._epoch, tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps))
 
     def _get_engine(self, batch, device, build):
         key = (batch, str(device), self.precision)
         ent = self._engines.get(key)
         if ent is None:
-            ent = {'eng': build(), 'ver': None}
+            ent = {'eng': build(), 'key': None}
             self._engines[key] = ent
-        v = self._version()
-        if ent['ver'] != v:
-            ent['eng'].load_state_dict({k: p for k, p in self.named_parameters()})
-            ent['ver'] = v
+        k = self._param_key()
+        if self.training or ent['key'] != k:
+            ent['eng'].load_state_dict({n: p for n, p in self.named_parameters()})
+            ent['key'] = k
         return ent['eng']
+
+    def load_state_dict(self, *a, **kw):
+        self.mark_dirty()
+        return super().load_state_dict(*a, **kw)
 
     def _apply(self, fn, *a, **kw):  # .to()/.cuda() invalidate engines
         self._engines = {}
+        self._epoch += 1
         return super()._apply(fn, *a, **kw)
 
 
@@ -116,7 +132,8 @@ class NCSNpp(_EngineModule):
                 _default_init_(p.data, 0.0 if zero_scale else 1.0)
 
     def forward(self, x, time_cond, z):
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+        dropout_live = self.training and float(self.cfg.dropout) > 0     # the fused inference plan has no dropout masks
+        if dropout_live or (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))):
             from . import train_graph
             return train_graph.generator_forward(self, x, time_cond, z)
         eng = self._get_engine(x.shape[0], x.device, lambda: GeneratorEngine(self.cfg, x.shape[0], x.device, self.precision))

@@ -291,6 +291,7 @@ class StatsFn(Function):
         return ops.stats_fwd(x)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         x, = ctx.saved_tensors
         return ops.stats_bwd(x, g.to(torch.float32).contiguous())
@@ -305,6 +306,7 @@ class AffineActFn(Function):
         return ops.affine_act_fwd(x, scale, shift, act)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
         x, scale, shift = ctx.saved_tensors
         dx, sums = ops.affine_act_bwd(x, dy.contiguous(), scale, shift, ctx.act)
@@ -436,6 +438,8 @@ def generator_forward(mod, x, time_cond, z):
     if not (cfg.resblock_type == 'biggan' and cfg.embedding_type == 'positional' and cfg.progressive == 'none'
             and cfg.progressive_input in ('residual', 'none') and cfg.fir and cfg.conditional):
         raise NotImplementedError('training path covers the biggan / positional / fir configuration family')
+    if cfg.num_channels_dae % 32 != 0:
+        raise NotImplementedError('training path needs num_channels_dae % 32 == 0 (channel-concatenated skips are not padded)')
     P = dict(mod.named_parameters())
     prec = mod.precision
     N, S = x.shape[0], cfg.image_size
@@ -563,6 +567,8 @@ def generator_forward(mod, x, time_cond, z):
 # ------------------------------------------------------------------------------------------------------------------
 def discriminator_forward(mod, x, t, x_t):
     """Discriminator_small/large.forward (discriminator.py:134-167 / :205-238), training path (double-differentiable)."""
+    if (8 * mod.ngf) % 32 != 0:
+        raise NotImplementedError('training path needs ngf % 4 == 0 (the stddev channel is appended after 8*ngf unpadded channels)')
     P = dict(mod.named_parameters())
     prec = mod.precision
     N, S = x.shape[0], x.shape[-1]

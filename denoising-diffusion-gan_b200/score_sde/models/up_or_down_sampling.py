@@ -2,7 +2,6 @@
 Inside the fused engines these are folded into PNHWC kernels; the functions here serve external callers and tests."""
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 from score_sde.op import upfirdn2d
 
@@ -48,14 +47,3 @@ def conv_downsample_2d(x, w, k=None, factor=2, gain=1):
     y = TG.conv_downsample_pnhwc(xp, w, None, n, h, wd)
     return TG.FromPnhwcFn.apply(y, _outC)
 
-
-
-def naive_upsample_2d(x, factor=2):
-    _N, C, H, W = x.shape
-    x = torch.reshape(x, (-1, C, H, 1, W, 1)).repeat(1, 1, 1, factor, 1, factor)
-    return torch.reshape(x, (-1, C, H * factor, W * factor))
-
-
-def naive_downsample_2d(x, factor=2):
-    _N, C, H, W = x.shape
-    return torch.mean(torch.reshape(x, (-1, C, H // factor, factor, W // factor, factor)), dim=(3, 5))

@@ -211,10 +211,12 @@ int ddg_stats_bwd(const float* x, const float* g, float* dx, int N, int H, int W
 int ddg_grad_norm_sq(const float* g, long n, double* out, cudaStream_t stream);
 /* One Adam step (torch.optim.Adam semantics, no amsgrad) over flat arenas with the gradient clipped to max_norm using
  * *normsq (NULL or max_norm <= 0: no clipping) and, when ema != NULL, ema = decay*ema + (1-decay)*p_new.
- * state: device float[2] = {step count (incremented by the call), learning rate}. */
+ * state: device float[2] = {step count (incremented by the call), learning rate}.
+ * grad_scale multiplies the gradient (and its norm) first: 1/world_size after a sum all-reduce of the arena (ddgan.py:363-365
+ * DistributedDataParallel averages), 1 otherwise. */
 int ddg_adam_ema_step(float* p, const float* g, float* m, float* v, float* ema, long n, float* state, const double* normsq,
                       float max_norm, float beta1, float beta2, float eps, float weight_decay, float ema_decay,
-                      cudaStream_t stream);
+                      float grad_scale, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

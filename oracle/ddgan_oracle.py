@@ -127,7 +127,7 @@ def conv_downsample_2d(x, w, k=(1, 3, 3, 1), factor: int = 2, gain: float = 1.0)
 def timestep_embedding(t: torch.Tensor, dim: int, max_positions: int = 10000) -> torch.Tensor:
     """score_sde/models/layers.py:475-486: [sin | cos] of t * exp(-j ln(max)/(half-1))."""
     half = dim // 2
-    freq = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(max_positions) / (half - 1)))
+    freq = torch.exp(torch.arange(half, dtype=torch.float32, device=t.device) * -(math.log(max_positions) / (half - 1)))
     arg = t.float()[:, None] * freq[None, :]
     emb = torch.cat([torch.sin(arg), torch.cos(arg)], dim=1)
     if dim % 2 == 1:
@@ -323,19 +323,26 @@ def down_conv_block(x, t_emb, sd, prefix, downsample, fir_kernel=(1, 3, 3, 1)):
     return (out + skip) * RSQRT2
 
 
-def discriminator_forward(sd: dict, x, t, x_t, t_emb_dim: int, large: bool = False):
-    """score_sde/models/discriminator.py:134-167 (small) / :205-238 (large)."""
-    te = timestep_embedding(t, t_emb_dim)
+def discriminator_forward(sd: dict, x, t, x_t, t_emb_dim: int, large: bool = False, stages: list = None):
+    """score_sde/models/discriminator.py:134-167 (small) / :205-238 (large).  `stages` (test aid): a list that receives the
+    output of start_conv, of every DownConvBlock, of final_conv (after the activation) and the pooled feature vector.
+    Runs in the dtype of `x` (float64 inputs and weights give the float64 ground truth; the sinusoid table stays the
+    reference's float32 one)."""
+    te = timestep_embedding(t, t_emb_dim).to(x.dtype)
     te = F.linear(te, sd['t_embed.main.0.weight'], sd['t_embed.main.0.bias'])
     te = F.linear(_leaky(te), sd['t_embed.main.2.weight'], sd['t_embed.main.2.bias'])
     te = _leaky(te)
     h = F.conv2d(torch.cat((x, x_t), dim=1), sd['start_conv.weight'], sd['start_conv.bias'])
+    if stages is not None:
+        stages.append(h)
     if large:
         flags = [True] * 6
     else:
         flags = [False, True, True, True]
     for i, ds in enumerate(flags):
         h = down_conv_block(h, te, sd, f'conv{i + 1}.', ds)
+        if stages is not None:
+            stages.append(h)
     b, c, hh, ww = h.shape
     group = min(b, 4)
     # minibatch stddev, :150-158: sample i is grouped with i + B/group, i + 2B/group, ...
@@ -344,7 +351,11 @@ def discriminator_forward(sd: dict, x, t, x_t, t_emb_dim: int, large: bool = Fal
     sdv = sdv.repeat(group, 1, hh, ww)
     h = torch.cat([h, sdv], 1)
     h = _leaky(F.conv2d(h, sd['final_conv.weight'], sd['final_conv.bias'], padding=1))
+    if stages is not None:
+        stages.append(h)
     h = h.view(b, h.shape[1], -1).sum(2)
+    if stages is not None:
+        stages.append(h)
     return F.linear(h, sd['end_linear.weight'], sd['end_linear.bias'])
 
 

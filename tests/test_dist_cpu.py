@@ -34,7 +34,21 @@ def _worker(rank, world, port, q):
     ref.load_state_dict(net.state_dict())
     (ref(data).mean() + (ref(data) ** 2).mean() + ref(data * 2).mean()).backward()
     err = max(float((a - b.grad).abs().max()) for a, b in zip(grads, ref.parameters()))
-    q.put((rank, err, float(sum(p.sum() for p in net.parameters()))))
+    # The fused path (train.FlatAdam, what bench.py times): parameters and .grad are views into flat arenas, the collective is
+    # ONE sum all-reduce of the gradient arena, and the mean's 1/world rides in the optimiser pass as `grad_scale`.
+    from ddgan_b200.train import FlatAdam
+    net2 = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(), torch.nn.Linear(16, 1))
+    net2.load_state_dict(ref.state_dict())
+    fa = FlatAdam(net2, 1e-3, (0.5, 0.999), max_norm=1.0)
+    fa.grad_scale = 1.0 / world
+    fa.zero_grad()
+    net2(local).mean().backward()
+    (net2(local) ** 2).mean().backward()
+    net2(local * 2).mean().backward()
+    assert all(p.grad.data_ptr() == fa.flat_g.data_ptr() + 4 * off for p, (off, _) in zip(fa.params, fa.views))
+    dist.all_reduce(fa.flat_g)
+    err2 = max(float((p.grad * fa.grad_scale - b.grad).abs().max()) for p, b in zip(net2.parameters(), ref.parameters()))
+    q.put((rank, max(err, err2), float(sum(p.sum() for p in net.parameters()))))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -167,38 +167,6 @@ def test_adversarial_step_gradients_vs_reference(golden):
     assert abs(float(tot) - float(g['gradG_norm'])) < 5e-4 * float(g['gradG_norm'])
 
 
-def test_trainer_step_and_graph_replay_update_weights():
-    """Trainer.step (eager) and the whole-step CUDA graphs run the same update: after identical injected randomness is not
-    available under capture, check instead that both paths run, keep weights finite, and move them by a comparable amount."""
-    import copy
-    from ddgan_b200.train import Trainer
-    cfg, netG, netD = _nets()
-    for k, v in dict(lr_g=1.6e-4, lr_d=1.25e-4, beta1=0.5, beta2=0.9, r1_gamma=0.02, lazy_reg=2, grad_clip_norm=1.0,
-                     ema_decay=0.999, use_ema=True).items():
-        setattr(cfg, k, v)
-    netG2, netD2 = copy.deepcopy(netG), copy.deepcopy(netD)
-    real = torch.tanh(seeded((4, 3, 32, 32), 300)).to(DEV)
-    tr = Trainer(cfg, netG, netD, DEV)
-    assert tr.skip_discarded_g_backward
-    w0 = torch.cat([p.detach().flatten() for p in netG.parameters()]).clone()
-    for i in range(3):
-        errD, errG = tr.step(real, i)
-    w1 = torch.cat([p.detach().flatten() for p in netG.parameters()])
-    assert torch.isfinite(w1).all() and torch.isfinite(errD) and torch.isfinite(errG)
-    d_eager = float((w1 - w0).norm())
-    assert d_eager > 0
-    tr2 = Trainer(cfg, netG2, netD2, DEV)
-    tr2.capture((4, 3, 32, 32), warmup=3)
-    # capture() ran warm-up + capture-time steps; measure the displacement of three further graphed steps
-    wa = torch.cat([p.detach().flatten() for p in netG2.parameters()]).clone()
-    for i in range(3):
-        errD, errG = tr2.step_graphed(real, i)
-    wb = torch.cat([p.detach().flatten() for p in netG2.parameters()])
-    assert torch.isfinite(wb).all() and torch.isfinite(errD) and torch.isfinite(errG)
-    d_graph = float((wb - wa).norm())
-    assert 0.2 * d_eager < d_graph < 5 * d_eager, (d_eager, d_graph)
-
-
 def test_skipping_the_discarded_generator_backward_is_exact():
     """Losses and both parameter updates agree with and without the generator backward that ddgan.py:489 throws away (same
     injected randomness), up to the summation order of atomic reductions."""
