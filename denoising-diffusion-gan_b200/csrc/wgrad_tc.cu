@@ -548,12 +548,22 @@ extern "C" int ddg_conv2d_wgrad(const ddg_wgrad_desc* c, cudaStream_t stream) {
   d.gain = c->gain == 0.f ? 1.f : c->gain;
   d.prof = (long long*)c->debug_prof;
   const int prec = c->precision == 1 ? 1 : 3;
+  // one tap row per CTA: 3x3 -> 3 groups of 3, 2x2 -> 2 groups of 2, 1x1 -> 1 group
+  const int gt = c->ntaps == 9 ? 3 : (c->ntaps == 4 ? 2 : (c->ntaps <= 4 ? c->ntaps : 3));
   if (c->Cin_pad % 128 == 0) {
-    // one tap row per CTA: 3x3 -> 3 groups of 3, 2x2 -> 2 groups of 2, 1x1 -> 1 group
-    const int gt = c->ntaps == 9 ? 3 : (c->ntaps == 4 ? 2 : (c->ntaps <= 4 ? c->ntaps : 3));
     return prec == 3 ? launch_wgrad<3, 128, 64, 3>(d, c->Cout, c->Cin_pad, gt, stream)
                      : launch_wgrad<1, 128, 64, 3>(d, c->Cout, c->Cin_pad, gt, stream);
   }
-  return prec == 3 ? launch_wgrad<3, 32, 128, 2>(d, c->Cout, c->Cin_pad, c->ntaps, stream)
-                   : launch_wgrad<1, 32, 128, 2>(d, c->Cout, c->Cin_pad, c->ntaps, stream);
+  if (c->Cin_pad % 64 == 0) {
+    // 64-channel maps (the 256-px NCSN++ configurations, ch = 64): N = 64 per tap, one tap row per CTA
+    return prec == 3 ? launch_wgrad<3, 64, 64, 3>(d, c->Cout, c->Cin_pad, gt, stream)
+                     : launch_wgrad<1, 64, 64, 3>(d, c->Cout, c->Cin_pad, gt, stream);
+  }
+  // narrow inputs (image convs, stddev channel): all taps per CTA while the X window (KT + span rows) fits, else one tap row
+  int rc = prec == 3 ? launch_wgrad<3, 32, 128, 2>(d, c->Cout, c->Cin_pad, c->ntaps, stream)
+                     : launch_wgrad<1, 32, 128, 2>(d, c->Cout, c->Cin_pad, c->ntaps, stream);
+  if (rc == DDG_ERR_UNSUPPORTED && gt < c->ntaps)
+    rc = prec == 3 ? launch_wgrad<3, 32, 128, 2>(d, c->Cout, c->Cin_pad, gt, stream)
+                   : launch_wgrad<1, 32, 128, 2>(d, c->Cout, c->Cin_pad, gt, stream);
+  return rc;
 }

@@ -251,6 +251,12 @@ def test_graphed_train_step_equals_eager_step(which):
         assert O.rel_l2(b.optD.flat_p.cpu(), a.optD.flat_p.cpu()) < 1e-5, it
         assert O.rel_l2(b.optG.flat_p.cpu(), a.optG.flat_p.cpu()) < 1e-5, it
         assert O.rel_l2(b.optG.ema.cpu(), a.optG.ema.cpu()) < 1e-5, it
+        # every iteration is compared from identical state: GAN training amplifies the 1e-7 differences of step k in step
+        # k + 1 (gate flips), which would make a 3-step trajectory test measure chaos rather than the graph
+        for oa, ob in ((a.optD, b.optD), (a.optG, b.optG)):
+            for ta, tb in ((oa.flat_p, ob.flat_p), (oa.m, ob.m), (oa.v, ob.v), (oa.state, ob.state)):
+                tb.copy_(ta)
+        b.optG.ema.copy_(a.optG.ema)
     assert float(a.optG.state[0]) == 3.0 and float(b.optG.state[0]) == 3.0
 
 
@@ -346,3 +352,48 @@ def test_trainer_reads_reference_optimizer_arguments():
     real = torch.tanh(seeded((4, 3, 32, 32), 300)).to(DEV)
     eD, eG = tr.step(real, 0)
     assert torch.isfinite(eD) and torch.isfinite(eG)
+
+
+def test_discriminator_large_r1_step_gradients_vs_oracle():
+    """BASELINE configs[3] path: Discriminator_large on 256-px inputs, D-real loss + R1 penalty (gamma 1.0) with the double
+    backward through six FIR-downsampling blocks, and the fake-sample loss; losses and every gradient tensor against CPU
+    autograd through the oracle (ngf 8 keeps the CPU side fast; 16/32/64-channel maps = narrow-map and N = 64 wgrad paths).
+    Tolerances as in the CIFAR step test: losses 1e-4, R1 5e-4, whole gradient 5e-4, live tensors 2e-3."""
+    from ddgan_b200.modules import Discriminator_large
+    B, ngf, ted, gamma = 2, 8, 32, 1.0
+    shapes = O.discriminator_param_shapes(6, ngf, ted, large=True)
+    sd = O.randomize_params(shapes, seed=71)
+    x_t = seeded((B, 3, 256, 256), 710); x_tp1 = seeded((B, 3, 256, 256), 711); x_fake = seeded((B, 3, 256, 256), 712)
+    t = torch.tensor([1, 3])
+    # ---- oracle ----
+    pd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xr = x_t.clone().requires_grad_(True)
+    d_real = O.discriminator_forward(pd, xr, t, x_tp1, ted, large=True).view(-1)
+    er = F.softplus(-d_real).mean()
+    g, = torch.autograd.grad(d_real.sum(), xr, create_graph=True)
+    gp = gamma / 2 * (g.view(B, -1).norm(2, dim=1) ** 2).mean()
+    ef = F.softplus(O.discriminator_forward(pd, x_fake, t, x_tp1, ted, large=True).view(-1)).mean()
+    (er + gp + ef).backward()
+    ref = {k: v.grad.clone() for k, v in pd.items()}
+    # ---- this framework: ddgan.py:455-477 on the drop-in module ----
+    net = Discriminator_large(nc=6, ngf=ngf, t_emb_dim=ted).to(DEV)
+    net.load_state_dict(sd, strict=True)
+    xd = x_t.to(DEV).requires_grad_(True); td = t.to(DEV)
+    D_real = net(xd, td, x_tp1.to(DEV)).view(-1)
+    errD_real = F.softplus(-D_real).mean()
+    errD_real.backward(retain_graph=True)
+    grad_real = torch.autograd.grad(outputs=D_real.sum(), inputs=xd, create_graph=True)[0]
+    grad_penalty = gamma / 2 * (grad_real.view(B, -1).norm(2, dim=1) ** 2).mean()
+    grad_penalty.backward()
+    errD_fake = F.softplus(net(x_fake.to(DEV), td, x_tp1.to(DEV)).view(-1)).mean()
+    errD_fake.backward()
+    assert abs(float(errD_real) - float(er)) < 1e-4 * max(1.0, abs(float(er)))
+    assert abs(float(errD_fake) - float(ef)) < 1e-4 * max(1.0, abs(float(ef)))
+    assert abs(float(grad_penalty) - float(gp)) < 5e-4 * abs(float(gp))
+    got = {k: p.grad.detach().cpu() for k, p in net.named_parameters()}
+    keys = list(ref)
+    flat = lambda d: torch.cat([d[k].flatten().double() for k in keys])
+    total = float(flat(ref).norm())
+    assert O.rel_l2(flat(got), flat(ref)) < 5e-4
+    worst = max((O.rel_l2(got[k], ref[k]), k) for k in keys if float(ref[k].double().norm()) > 1e-6 * total)
+    assert worst[0] < 2e-3, worst

@@ -18,7 +18,9 @@ def seeded(shape, seed, scale=1.0):
 
 
 @pytest.mark.parametrize('n,cin,cout,h,k', [(2, 32, 64, 8, 3), (4, 64, 128, 16, 3), (3, 128, 32, 8, 1), (2, 256, 256, 4, 3), (8, 128, 128, 32, 3),
-                                            (32, 128, 128, 32, 3)])   # bench-scale: persistent fwd / dgrad kernels, clustered split-K wgrad
+                                            (32, 128, 128, 32, 3),    # bench-scale: persistent fwd / dgrad kernels, clustered split-K wgrad
+                                            (2, 64, 64, 32, 3), (1, 64, 128, 256, 3),   # 64-channel maps of the 256-px configs (N = 64 wgrad tiles)
+                                            (1, 32, 64, 256, 3)])     # narrow input at 256 px: wgrad falls back to one tap row per CTA
 def test_conv_grads_and_double_backward(n, cin, cout, h, k):
     from ddgan_b200 import train_graph as TG
     x = seeded((n, cin, h, h), 1); w = seeded((cout, cin, k, k), 2) / math.sqrt(cin * k * k); b = seeded((cout,), 3, 0.1)

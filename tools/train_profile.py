@@ -1,4 +1,4 @@
-"""torch.profiler breakdown of one train step (kernel time by name, and CPU vs GPU time)."""
+"""torch.profiler breakdown of one train step (kernel time and launch counts by name, CPU ops by count)."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'denoising-diffusion-gan_b200'))
@@ -17,19 +17,21 @@ torch.cuda.synchronize()
 t0 = time.perf_counter()
 for i in range(1, 6): tr.step(real, i)
 torch.cuda.synchronize()
-print('plain step ms', (time.perf_counter() - t0) / 5 * 1e3)
+print('plain step ms (eager)', (time.perf_counter() - t0) / 5 * 1e3)
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for i in range(1, 3): tr.step(real, i)
     torch.cuda.synchronize()
 ev = prof.key_averages()
-rows = sorted([e for e in ev if e.device_time_total > 0], key=lambda e: -e.device_time_total)
-tot = sum(e.self_device_time_total for e in ev)
-print('total device time per step (ms):', tot / 2 / 1e3)
-for e in rows[:40]:
-    if e.self_device_time_total > 0:
-        print(f'{e.self_device_time_total/2/1e3:9.3f} ms x{e.count//2:5d}  {e.key[:100]}')
-print('--- by launch count ---')
-kern = [e for e in ev if e.self_device_time_total > 0 and not e.key.endswith('Fn') and not e.key.endswith('Backward') and not e.key.startswith('aten::')]
-for e in sorted(kern, key=lambda e: -e.count)[:28]:
-    print(f'x{e.count//2:5d} {e.self_device_time_total/2/1e3:8.3f} ms  {e.key[:110]}')
-print('kernel launches per step:', sum(e.count for e in kern) // 2)
+kern = [e for e in ev if e.self_device_time_total > 0 and e.device_type.name == 'CUDA']
+tot = sum(e.self_device_time_total for e in kern)
+print('total kernel time per step (ms):', tot / 2 / 1e3, ' launches per step:', sum(e.count for e in kern) // 2)
+print('--- kernels by time ---')
+for e in sorted(kern, key=lambda e: -e.self_device_time_total)[:40]:
+    print(f'{e.self_device_time_total/2/1e3:9.3f} ms x{e.count//2:5d}  {e.key[:110]}')
+print('--- kernels by launch count ---')
+for e in sorted(kern, key=lambda e: -e.count)[:70]:
+    print(f'x{e.count//2:5d} {e.self_device_time_total/2/1e3:8.3f} ms  {e.key[:120]}')
+print('--- CPU-side ops by count (aten:: / autograd Functions) ---')
+cpu = [e for e in ev if e.device_type.name == 'CPU']
+for e in sorted(cpu, key=lambda e: -e.count)[:60]:
+    print(f'x{e.count//2:5d}  {e.key[:100]}')
