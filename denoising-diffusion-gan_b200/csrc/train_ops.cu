@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) pnhwc_reduce_kernel(const float* __restri
         gg = g.y * act_d(fmaf(v.y, s.y, t.y), act); a1[1] += gg * v.y; a2[1] += gg; o.y = gg * s.y;
         gg = g.z * act_d(fmaf(v.z, s.z, t.z), act); a1[2] += gg * v.z; a2[2] += gg; o.z = gg * s.z;
         gg = g.w * act_d(fmaf(v.w, s.w, t.w), act); a1[3] += gg * v.w; a2[3] += gg; o.w = gg * s.w;
-        stg_stream(reinterpret_cast<float4*>(dx + off), o);
+        if (dx) stg_stream(reinterpret_cast<float4*>(dx + off), o);
       } else {
         a1[0] += v.x; a2[0] += v.x * v.x; a1[1] += v.y; a2[1] += v.y * v.y;
         a1[2] += v.z; a2[2] += v.z * v.z; a1[3] += v.w; a2[3] += v.w * v.w;
@@ -117,9 +117,97 @@ __global__ void __launch_bounds__(256) stats_bwd_kernel(const float* __restrict_
   }
 }
 
+// GroupNorm backward, second pass: dx = dy * act'(scale*x + shift) * scale + g1[n,c] + 2 * x * g2[n,c]
+// (the first term is the path through the affine + activation, the other two the path through the statistics)
+__global__ void __launch_bounds__(256) gn_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                       const float* __restrict__ scale, const float* __restrict__ shift,
+                                                       const float* __restrict__ g12, float* __restrict__ dx, int N, int H, int W, int C,
+                                                       int act) {
+  const int C4 = C / 4;
+  const long total = (long)N * H * W * C4;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    long r = i / C4;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H);
+    const int n = (int)(r / H);
+    const size_t off = ((size_t)(n * (H + 2) + h + 1) * (W + 2) + (w + 1)) * C + c4 * 4;
+    const float4 v = ldg_stream(reinterpret_cast<const float4*>(x + off));
+    const float4 g = ldg_stream(reinterpret_cast<const float4*>(dy + off));
+    const float4 s = __ldg(reinterpret_cast<const float4*>(scale + (size_t)n * C) + c4);
+    const float4 t = __ldg(reinterpret_cast<const float4*>(shift + (size_t)n * C) + c4);
+    const float* gp = g12 + ((size_t)n * C + c4 * 4) * 2;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp));      // g1[c], g2[c], g1[c+1], g2[c+1]
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gp) + 1);
+    float4 o;
+    o.x = g.x * act_d(fmaf(v.x, s.x, t.x), act) * s.x + g0.x + 2.f * v.x * g0.y;
+    o.y = g.y * act_d(fmaf(v.y, s.y, t.y), act) * s.y + g0.z + 2.f * v.y * g0.w;
+    o.z = g.z * act_d(fmaf(v.z, s.z, t.z), act) * s.z + g1.x + 2.f * v.z * g1.y;
+    o.w = g.w * act_d(fmaf(v.w, s.w, t.w), act) * s.w + g1.z + 2.f * v.w * g1.w;
+    stg_stream(reinterpret_cast<float4*>(dx + off), o);
+  }
+}
+
+// one thread per (sample, group): from the forward statistics and the first-pass sums {sum gg*x, sum gg} (gg = dy * act'(u)):
+// d(gamma), d(beta) per (n, c) and the coefficients g1 = d(sum x), g2 = d(sum x^2) of the second pass.
+__global__ void gn_bwd_coeffs_kernel(const double* __restrict__ st, const double* __restrict__ sums, const float* __restrict__ gamma,
+                                     int gb_stride, int per_sample, float* __restrict__ g12, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, int dgb_stride, int N, int C, int HW, int G, float eps) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * G) return;
+  const int n = idx / G, g = idx - n * G;
+  const int cpg = C / G;
+  const size_t base = (size_t)n * C + (size_t)g * cpg;
+  double s1 = 0, s2 = 0;
+  for (int j = 0; j < cpg; ++j) { s1 += st[(base + j) * 2]; s2 += st[(base + j) * 2 + 1]; }
+  const double cnt = (double)cpg * HW;
+  const double mean = s1 / cnt;
+  double var = s2 / cnt - mean * mean;
+  const bool clamped = var < 0;
+  if (clamped) var = 0;
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  double d_rstd = 0, d_mean = 0;
+  for (int j = 0; j < cpg; ++j) {
+    const int c = g * cpg + j;
+    const double ga = gamma ? (double)(per_sample ? gamma[(size_t)n * gb_stride + c] : gamma[c]) : 1.0;
+    const double ds = sums[(base + j) * 2], dh = sums[(base + j) * 2 + 1];   // d(scale), d(shift)
+    const double t = ds - mean * dh;                 // scale = ga*rstd, shift = be - mean*ga*rstd
+    dgamma[(size_t)n * dgb_stride + c] = (float)(rstd * t);
+    dbeta[(size_t)n * dgb_stride + c] = (float)dh;
+    d_rstd += ga * t;
+    d_mean -= rstd * ga * dh;
+  }
+  const double d_var = clamped ? 0.0 : -0.5 * d_rstd * rstd * rstd * rstd;
+  const float d_s1 = (float)(d_mean / cnt - 2.0 * mean * d_var / cnt);
+  const float d_s2 = (float)(d_var / cnt);
+  for (int j = 0; j < cpg; ++j) { g12[(base + j) * 2] = d_s1; g12[(base + j) * 2 + 1] = d_s2; }
+}
+
 }  // namespace ddg
 
 using namespace ddg;
+
+extern "C" int ddg_gn_bwd_dx(const float* x, const float* dy, const float* scale, const float* shift, const float* g12, float* dx, int N,
+                             int H, int W, int C, int act, cudaStream_t stream) {
+  if (!x || !dy || !scale || !shift || !g12 || !dx || C % 4 != 0) { ddg_set_last_error("gn_bwd_dx: bad args"); return DDG_ERR_ARG; }
+  const long total = (long)N * H * W * (C / 4);
+  long blocks = (total + 255) / 256;
+  if (blocks > 148L * 32) blocks = 148L * 32;
+  gn_bwd_dx_kernel<<<(int)blocks, 256, 0, stream>>>(x, dy, scale, shift, g12, dx, N, H, W, C, act);
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}
+
+extern "C" int ddg_gn_bwd_coeffs(const double* stats, const double* sums, const float* gamma, int gb_stride, int per_sample, float* g12,
+                                 float* dgamma, float* dbeta, int dgb_stride, int N, int C, int HW, int G, float eps,
+                                 cudaStream_t stream) {
+  if (!stats || !sums || !g12 || !dgamma || !dbeta || G <= 0 || C % G != 0) { ddg_set_last_error("gn_bwd_coeffs: bad args"); return DDG_ERR_ARG; }
+  const int total = N * G;
+  gn_bwd_coeffs_kernel<<<(total + 127) / 128, 128, 0, stream>>>(stats, sums, gamma, gb_stride, per_sample, g12, dgamma, dbeta,
+                                                               dgb_stride, N, C, HW, G, eps);
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}
 
 static int reduce_launch_cfg(int H, int W, int C, int& threads, int& pix_per_block, int& blocks, size_t& smem) {
   const int C4 = C / 4;
@@ -149,7 +237,7 @@ extern "C" int ddg_affine_act_fwd(const float* x, const float* scale, const floa
 
 extern "C" int ddg_affine_act_bwd(const float* x, const float* dy, const float* scale, const float* shift, float* dx, double* sums, int N,
                                   int H, int W, int C, int act, cudaStream_t stream) {
-  if (!x || !dy || !dx || ((scale == nullptr) != (shift == nullptr))) { ddg_set_last_error("affine_act_bwd: bad args"); return DDG_ERR_ARG; }
+  if (!x || !dy || (!dx && !sums) || ((scale == nullptr) != (shift == nullptr))) { ddg_set_last_error("affine_act_bwd: bad args"); return DDG_ERR_ARG; }
   int threads, ppb, blocks; size_t smem;
   if (reduce_launch_cfg(H, W, C, threads, ppb, blocks, smem)) { ddg_set_last_error("affine_act_bwd: unsupported channel count"); return DDG_ERR_UNSUPPORTED; }
   static bool attr = false;

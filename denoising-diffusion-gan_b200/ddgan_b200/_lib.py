@@ -37,6 +37,13 @@ class WgradDesc(C.Structure):
                 ('tap_ds', C.c_int8 * 9), ('s_co', C.c_long), ('s_ci', C.c_long), ('s_tap', C.c_long), ('precision', C.c_int), ('gain', C.c_float), ('debug_prof', C.c_void_p)]
 
 
+class PackItem(C.Structure):
+    _fields_ = [('w', C.c_void_p), ('out', C.c_void_p), ('s_co', C.c_long), ('s_ci', C.c_long), ('s_tap', C.c_long),
+                ('chunk_begin', C.c_long), ('cout', C.c_int), ('cin_real', C.c_int), ('cin_pad', C.c_int), ('ntaps', C.c_int),
+                ('flip_taps', C.c_int), ('kb', C.c_int), ('stage_offset', C.c_int), ('total_stages', C.c_int),
+                ('precision', C.c_int), ('nt', C.c_int)]
+
+
 MLP_MAX_LAYERS = 8
 
 
@@ -74,10 +81,17 @@ _SIGNATURES = {
     'ddg_conv_set_nt256': ([_I], _I),
     'ddg_conv_packed_bytes': ([_I, _I, _I, _I, _I], _L),
     'ddg_conv_pack_weights': ([_P, _P, _I, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _I, _I, _I, _L, _P], _I),
+    'ddg_conv_pack_chunks': ([_I] * 5, _L),
+    'ddg_conv_pack_batch': ([_P, _I, _L, _P], _I),
+    'ddg_channel_grads_splits': ([_I] * 4, _I),
+    'ddg_channel_grads': ([_P, _P, _P] + [_I] * 5 + [_F, _I, _P], _I),
+    'ddg_s2d_weights': ([_P, _P, _I, _I, _I, _I, _P], _I),
     'ddg_conv2d_fwd': ([C.POINTER(ConvDesc), _P], _I),
     'ddg_conv2d_wgrad': ([C.POINTER(WgradDesc), _P], _I),
     'ddg_affine_act_fwd': ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
     'ddg_affine_act_bwd': ([_P] * 6 + [_I] * 5 + [_P], _I),
+    'ddg_gn_bwd_coeffs': ([_P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P], _I),
+    'ddg_gn_bwd_dx': ([_P] * 6 + [_I] * 5 + [_P], _I),
     'ddg_stats_fwd': ([_P, _P, _I, _I, _I, _I, _P], _I),
     'ddg_stats_bwd': ([_P, _P, _P, _I, _I, _I, _I, _P], _I),
     'ddg_grad_norm_sq': ([_P, _L, _P, _P], _I),

@@ -41,12 +41,23 @@ def _groups(c):
 
 
 class _EngineBase:
-    def __init__(self, batch, device, precision, shapes):
+    def __init__(self, batch, device, precision, shapes, params=None):
+        """params: optional {name: tensor} whose storage the engine reads directly (the drop-in modules pass their own
+        parameters: no per-update copies; the caller rebuilds the engine if those tensors move).  Default: engine-owned
+        fixed-address copies filled by load_state_dict."""
         self.N = batch
         self.dev = torch.device(device)
         self.prec = precision
         self.shapes = shapes
-        self.P = {k: torch.zeros(v, device=self.dev) for k, v in shapes.items()}  # fixed-address parameter copies
+        if params is not None:
+            self.P = {}
+            for k, v in shapes.items():
+                t = params[k].detach()
+                assert tuple(t.shape) == tuple(v) and t.is_contiguous() and t.device == self.dev and t.dtype == torch.float32, k
+                self.P[k] = t
+        else:
+            self.P = {k: torch.zeros(v, device=self.dev) for k, v in shapes.items()}  # fixed-address parameter copies
+        self._pack_plan = None
         self.steps = []      # zero-arg callables, executed in order on the current stream
         self.step_names = []
         self.binders = []    # zero-arg callables that (re)pack derived weights from self.P
@@ -120,14 +131,20 @@ class _EngineBase:
         if strict and (missing or extra):
             raise KeyError(f'state_dict mismatch: missing {missing[:4]}..., unexpected {extra[:4]}...')
         for k, buf in self.P.items():
-            if k in sd:
+            if k in sd and sd[k].data_ptr() != buf.data_ptr():
                 buf.copy_(sd[k].detach().reshape(buf.shape))
         self.refresh()
 
     def refresh(self):
-        """Re-derive packed operands after self.P changed (weight update)."""
-        for b in self.binders:
-            b()
+        """Re-derive packed operands after self.P changed (weight update): the binders' small copies, then every B-operand pack
+        of the plan as one launch (recorded on the first refresh)."""
+        first = self._pack_plan is None
+        if first:
+            self._pack_plan = ops.PackPlan()
+        with ops.pack_context(self._pack_plan, 'record' if first else 'skip'):
+            for b in self.binders:
+                b()
+        self._pack_plan.run()
 
     def run_steps(self):
         for s in self.steps:
@@ -150,13 +167,13 @@ class _EngineBase:
 
 
 class GeneratorEngine(_EngineBase):
-    def __init__(self, cfg, batch, device='cuda', precision=3):
+    def __init__(self, cfg, batch, device='cuda', precision=3, params=None):
         cfg = arch.normalize_config(cfg)
         if not (cfg.resblock_type == 'biggan' and cfg.embedding_type == 'positional' and cfg.progressive == 'none'
                 and cfg.progressive_input in ('residual', 'none') and cfg.fir and cfg.conditional
                 and tuple(cfg.fir_kernel) == (1, 3, 3, 1) and cfg.num_channels_dae % 32 == 0):
             raise NotImplementedError('GeneratorEngine covers the biggan / positional / fir configuration family (README configs)')
-        super().__init__(batch, device, precision, arch.ncsnpp_param_shapes(cfg))
+        super().__init__(batch, device, precision, arch.ncsnpp_param_shapes(cfg), params=params)
         self.cfg = cfg
         self._build()
 
@@ -188,14 +205,14 @@ class GeneratorEngine(_EngineBase):
         self._w_style = torch.empty(jt, zd, device=dev); self._b_style = torch.empty(jt, device=dev)
         self._w_dense = torch.empty(jd, 4 * nf, device=dev); self._b_dense = torch.empty(jd, device=dev)
 
-        def bind_proj():
-            for nme in self._style_names:
-                o = self._style_off[nme]; j = self.shapes[nme + '.weight'][0]
-                self._w_style[o:o + j].copy_(P[nme + '.weight']); self._b_style[o:o + j].copy_(P[nme + '.bias'])
-            for nme in self._dense_names:
-                o = self._dense_off[nme]; j = self.shapes[nme + '.weight'][0]
-                self._w_dense[o:o + j].copy_(P[nme + '.weight']); self._b_dense[o:o + j].copy_(P[nme + '.bias'])
-        self.binders.append(bind_proj)
+        dsts, srcs = [], []
+        for nme in self._style_names:
+            o = self._style_off[nme]; j = self.shapes[nme + '.weight'][0]
+            dsts += [self._w_style[o:o + j], self._b_style[o:o + j]]; srcs += [P[nme + '.weight'], P[nme + '.bias']]
+        for nme in self._dense_names:
+            o = self._dense_off[nme]; j = self.shapes[nme + '.weight'][0]
+            dsts += [self._w_dense[o:o + j], self._b_dense[o:o + j]]; srcs += [P[nme + '.weight'], P[nme + '.bias']]
+        self.binders.append(lambda: torch._foreach_copy_(dsts, srcs))     # a few multi-tensor launches for the 168 slices
 
         used_holder = [0]
         self._step(lambda: self._stats_arena[:used_holder[0]].zero_())
@@ -411,14 +428,7 @@ class GeneratorEngine(_EngineBase):
         w2 = torch.zeros(cout, 2, 2, cp, 2, 2, device=self.dev)
 
         def bind(cw):
-            w = Pm[Pn + '.weight']                       # [Cout, Cin, 3, 3]
-            for dy in range(2):
-                for dx in range(2):
-                    for py in range(2):
-                        for px in range(2):
-                            r, s_ = 2 * dy + py, 2 * dx + px
-                            if r < 3 and s_ < 3:
-                                w2[:, py, px, :cin_real, dy, dx].copy_(w[:, :, r, s_])
+            ops.s2d_weights(Pm[Pn + '.weight'], cout, cin_real, cp, out=w2)       # [Cout, Cin, 3, 3] -> [Cout, 2, 2, cp, 2, 2]
             cw.pack_segment(0, w2, 4 * cp, 4 * cp * 4, 4, 1)
         scale = RSQRT2 if self.cfg.skip_rescale else 1.0
         self._conv(cout, [ops.conv_src(s2d, 4 * cp, ops.TAPS_2X2)], Ho, Wo, out.buf, bind, hp=Ho + 3, wp=Wo + 3,
@@ -438,8 +448,8 @@ class GeneratorEngine(_EngineBase):
 class DiscriminatorEngine(_EngineBase):
     """Discriminator_small / Discriminator_large forward (discriminator.py:134-167 / :205-238), act = LeakyReLU(0.2)."""
 
-    def __init__(self, nc, ngf, t_emb_dim, image_size, batch, large=False, device='cuda', precision=3):
-        super().__init__(batch, device, precision, arch.discriminator_param_shapes(nc, ngf, t_emb_dim, large))
+    def __init__(self, nc, ngf, t_emb_dim, image_size, batch, large=False, device='cuda', precision=3, params=None):
+        super().__init__(batch, device, precision, arch.discriminator_param_shapes(nc, ngf, t_emb_dim, large), params=params)
         self.nc, self.ngf, self.t_emb_dim, self.S, self.large = nc, ngf, t_emb_dim, image_size, large
         # narrow maps (2*ngf, 4*ngf not multiples of 32) live in buffers padded to 32 channels whose extra channels stay zero;
         # the minibatch-stddev / final_conv stage needs its 8*ngf channels unpadded

@@ -71,6 +71,7 @@ class _EngineModule(nn.Module):
     def __init__(self):
         super().__init__()
         self._engines = {}
+        self._engine_ptrs = None
         self._epoch = 0
         self.precision = 3  # 3 = BF16x3 (fp32 parity), 1 = BF16
 
@@ -82,14 +83,19 @@ class _EngineModule(nn.Module):
         return (self._epoch, tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps))
 
     def _get_engine(self, batch, device, build):
+        """build(params) -> engine reading the module's own parameter storage (no copies per update).  If that storage moved
+        (FlatAdam re-homes the parameters into its arena, .to(...)), every cached engine is dropped and rebuilt."""
+        k = self._param_key()
+        if self._engines and self._engine_ptrs != k[2]:
+            self._engines = {}
         key = (batch, str(device), self.precision)
         ent = self._engines.get(key)
         if ent is None:
-            ent = {'eng': build(), 'key': None}
+            self._engine_ptrs = k[2]
+            ent = {'eng': build({n: p for n, p in self.named_parameters()}), 'key': None}
             self._engines[key] = ent
-        k = self._param_key()
         if self.training or ent['key'] != k:
-            ent['eng'].load_state_dict({n: p for n, p in self.named_parameters()})
+            ent['eng'].refresh()
             ent['key'] = k
         return ent['eng']
 
@@ -136,7 +142,8 @@ class NCSNpp(_EngineModule):
         if dropout_live or (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))):
             from . import train_graph
             return train_graph.generator_forward(self, x, time_cond, z)
-        eng = self._get_engine(x.shape[0], x.device, lambda: GeneratorEngine(self.cfg, x.shape[0], x.device, self.precision))
+        eng = self._get_engine(x.shape[0], x.device,
+                               lambda prm: GeneratorEngine(self.cfg, x.shape[0], x.device, self.precision, params=prm))
         return eng.forward(x, time_cond, z).clone()
 
 
@@ -163,9 +170,9 @@ class _Discriminator(_EngineModule):
             from . import train_graph
             return train_graph.discriminator_forward(self, x, t, x_t)
         S = x.shape[-1]
-        eng = self._get_engine(x.shape[0], x.device, lambda: DiscriminatorEngine(self.nc, self.ngf, self.t_emb_dim, S, x.shape[0],
-                                                                                 large=self.large, device=x.device,
-                                                                                 precision=self.precision))
+        eng = self._get_engine(x.shape[0], x.device,
+                               lambda prm: DiscriminatorEngine(self.nc, self.ngf, self.t_emb_dim, S, x.shape[0], large=self.large,
+                                                               device=x.device, precision=self.precision, params=prm))
         return eng.forward(x, t, x_t).clone()
 
 

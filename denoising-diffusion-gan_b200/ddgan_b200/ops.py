@@ -258,18 +258,33 @@ def affine_act_fwd(x, scale, shift, act, out=None):
     return out
 
 
-def affine_act_bwd(x, dy, scale, shift, act, need_sums=True):
+def affine_act_bwd(x, dy, scale, shift, act, need_sums=True, need_dx=True, sums=None):
+    """sums (float64 [N, C, 2], accumulated: pass a zeroed buffer or let one be allocated) = {sum gg*x, sum gg} with
+    gg = dy * act'(scale*x + shift); dx = gg * scale unless need_dx is False (first pass of the fused GroupNorm backward)."""
     n, hp, wp, c = x.shape
-    dx = empty_like_pnhwc(x)
-    sums = torch.zeros(n, c, 2, dtype=torch.float64, device=x.device) if need_sums else None
+    dx = empty_like_pnhwc(x) if need_dx else None
+    if sums is None and need_sums:
+        sums = torch.zeros(n, c, 2, dtype=torch.float64, device=x.device)
     check(lib().ddg_affine_act_bwd(ptr(x), ptr(dy), ptr(scale), ptr(shift), ptr(dx), ptr(sums), n, hp - 2, wp - 2, c, act, stream()),
           'affine_act_bwd')
     return dx, sums
 
 
-def stats_fwd(x):
+def gn_bwd_coeffs(stats, sums, gamma, gb_stride, per_sample, g12, dgamma, dbeta, dgb_stride, n, c, hw, groups, eps=1e-6):
+    check(lib().ddg_gn_bwd_coeffs(ptr(stats), ptr(sums), ptr(gamma), gb_stride, int(per_sample), ptr(g12), ptr(dgamma), ptr(dbeta),
+                                  dgb_stride, n, c, hw, groups, eps, stream()), 'gn_bwd_coeffs')
+
+
+def gn_bwd_dx(x, dy, scale, shift, g12, act):
     n, hp, wp, c = x.shape
-    st = torch.zeros(n, c, 2, dtype=torch.float64, device=x.device)
+    dx = empty_like_pnhwc(x)
+    check(lib().ddg_gn_bwd_dx(ptr(x), ptr(dy), ptr(scale), ptr(shift), ptr(g12), ptr(dx), n, hp - 2, wp - 2, c, act, stream()), 'gn_bwd_dx')
+    return dx
+
+
+def stats_fwd(x, out=None):
+    n, hp, wp, c = x.shape
+    st = out if out is not None else torch.zeros(n, c, 2, dtype=torch.float64, device=x.device)
     check(lib().ddg_stats_fwd(ptr(x), ptr(st), n, hp - 2, wp - 2, c, stream()), 'stats_fwd')
     return st
 
@@ -330,6 +345,41 @@ def gemm_tn(a, b, precision=3):
     return out
 
 
+def channel_grads(dy, cout, scale=1.0, need_dav=True, db_accum=None, need_db=True, dav_into=None):
+    """(dav [N, cout] or None, db [cout] or None) = scale * sums of the PNHWC gradient dy over (h, w) / over (n, h, w).
+    db_accum: accumulate the bias gradient straight into this tensor (a .grad view) instead of returning it.
+    dav_into = (address, row pitch): write the per-sample sums into a slice of a wider zero-initialised buffer instead."""
+    n, hp, wp, c = dy.shape
+    dav = db = None
+    dav_stride = cout
+    if dav_into is not None:
+        dav, dav_stride = dav_into
+    elif need_dav:
+        s = lib().ddg_channel_grads_splits(n, hp - 2, wp - 2, c)
+        dav = (torch.zeros if s > 1 else torch.empty)(n, cout, device=dy.device, dtype=torch.float32)
+    if db_accum is not None:
+        dbp = db_accum
+    elif need_db:
+        db = torch.zeros(cout, device=dy.device, dtype=torch.float32)
+        dbp = db
+    else:
+        dbp = None
+    if dav is None and dbp is None:
+        return None, None
+    check(lib().ddg_channel_grads(ptr(dy), ptr(dav), ptr(dbp), n, hp - 2, wp - 2, c, cout, scale, dav_stride, stream()), 'channel_grads')
+    return (None if dav_into is not None else dav), db
+
+
+def s2d_weights(src, cout, cin, cp, adjoint=False, out=None):
+    """conv_downsample_2d weights [Cout, Cin, 3, 3] <-> the 2x2-tap space-to-depth form [Cout, 2, 2, cp, 2, 2] (adjoint: gradient)."""
+    require_cuda_f32(src)
+    src = src.contiguous()
+    if out is None:
+        out = torch.empty((cout, cin, 3, 3) if adjoint else (cout, 2, 2, cp, 2, 2), device=src.device, dtype=torch.float32)
+    check(lib().ddg_s2d_weights(ptr(src), ptr(out), cout, cin, cp, int(adjoint), stream()), 's2d_weights')
+    return out
+
+
 def minibatch_stddev(x, out, group):
     n, hp, wp, c = x.shape
     check(lib().ddg_minibatch_stddev(ptr(x), ptr(out), n, hp - 2, wp - 2, c, out.shape[-1], group, stream()), 'minibatch_stddev')
@@ -352,6 +402,62 @@ def softmax_rows(s, p, rows, T, lds, ldp):
 # ---------------------------------------------------------------------------------------------------------
 # tcgen05 implicit-GEMM convolution
 # ---------------------------------------------------------------------------------------------------------
+class PackPlan:
+    """All weight packs of a network as ONE launch (ddg_conv_pack_batch): a device-resident table of pack items, recorded the
+    first time the packs are issued one by one and replayed afterwards.  Items point at fixed addresses (parameters in a flat
+    arena or engine-owned copies, packed buffers owned by ConvWeights objects that the plan keeps alive)."""
+
+    def __init__(self):
+        self.items = []
+        self.keep = []
+        self.table = None
+        self.total = 0
+
+    def add(self, cw, seg, w_addr, cin_real, s_co, s_ci, s_tap, flip):
+        c, nt = cw.segs[seg]
+        it = _lib.PackItem()
+        it.w = w_addr; it.out = cw.buf.data_ptr()
+        it.s_co, it.s_ci, it.s_tap = s_co, s_ci, s_tap
+        it.chunk_begin = self.total
+        it.cout, it.cin_real, it.cin_pad, it.ntaps, it.flip_taps = cw.cout, cin_real, c, nt, int(flip)
+        it.kb, it.stage_offset, it.total_stages, it.precision, it.nt = KB, cw.offsets[seg], cw.total_stages, cw.precision, cw.nt
+        self.total += lib().ddg_conv_pack_chunks(cw.cout, c, nt, KB, cw.nt)
+        self.items.append(it)
+        self.keep.append(cw)
+        self.table = None
+
+    def finalize(self, device):
+        if not self.items:
+            return
+        arr = (_lib.PackItem * len(self.items))(*self.items)
+        raw = bytes(arr)
+        self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+
+    def run(self):
+        if not self.items:
+            return
+        if self.table is None:
+            self.finalize(self.keep[0].buf.device)
+        check(lib().ddg_conv_pack_batch(ptr(self.table), len(self.items), self.total, stream()), 'conv_pack_batch')
+
+
+# Pack recorder: while set to (plan, mode), ConvWeights.pack_segment does not launch; mode 'record' appends the pack to the plan,
+# mode 'skip' assumes it is already in the plan (the caller runs plan.run() afterwards).
+_PACK_CTX = [None]
+
+
+class pack_context:
+    def __init__(self, plan, mode):
+        self.ctx = (plan, mode)
+
+    def __enter__(self):
+        self.prev = _PACK_CTX[0]
+        _PACK_CTX[0] = self.ctx
+
+    def __exit__(self, *a):
+        _PACK_CTX[0] = self.prev
+
+
 class ConvWeights:
     """Device-resident packed B operand of one fused convolution (all K segments, all n-tiles).
 
@@ -378,6 +484,11 @@ class ConvWeights:
         """B[co][ci][tap] = w.flat[elem_offset + co*s_co + ci*s_ci + tap*s_tap] for ci < cin_real (zero beyond)."""
         require_cuda_f32(w)
         c, nt = self.segs[i]
+        if _PACK_CTX[0] is not None and self.batch == 1:
+            plan, mode = _PACK_CTX[0]
+            if mode == 'record':
+                plan.add(self, i, w.data_ptr() + 4 * elem_offset, cin_real, s_co, s_ci, s_tap, flip)
+            return
         check(lib().ddg_conv_pack_weights(w.data_ptr() + 4 * elem_offset, ptr(self.buf), self.cout, cin_real, c, nt, s_co, s_ci, s_tap, int(flip),
                                           KB, self.offsets[i], self.total_stages, self.precision, self.nt, self.batch, w_batch_stride,
                                           stream()), 'conv_pack_weights')

@@ -282,6 +282,7 @@ class Trainer:
                 self.arG = FlatGradAllReducer(netG.parameters())
                 self.arD = FlatGradAllReducer(netD.parameters())
         self._graphs = None
+        self._packs_frozen = False
         self.noise_static = None
         self.ema = EMA(netG, ema_decay) if (not self.fused_optim and use_ema) else None
 
@@ -328,6 +329,21 @@ class Trainer:
         """One iteration of ddgan.py:443-518.  `noise` (parity runs / graph replays) = dict with t_d, n_xtp1_d, n_xt_d, z_d,
         n_post_d and the same with suffix _g; by default everything is drawn with torch's CUDA generator in the reference's
         order."""
+        from . import train_graph
+        # with the flat arenas every parameter owns its .grad for good: let the wgrad / bias-sum kernels accumulate into it
+        train_graph.ACCUM['on'] = self.fused_optim
+        try:
+            out = self._step(real_data, global_step, noise)
+        finally:
+            train_graph.ACCUM['on'] = False
+        if not self._packs_frozen:
+            # the first step recorded every weight pack of both networks; from now on one launch per network forward
+            train_graph.freeze_packs(self.netG)
+            train_graph.freeze_packs(self.netD)
+            self._packs_frozen = True
+        return out
+
+    def _step(self, real_data, global_step, noise=None):
         a, netG, netD = self.args, self.netG, self.netD
         nz = noise or {}
         B = real_data.size(0)

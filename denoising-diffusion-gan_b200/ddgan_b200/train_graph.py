@@ -57,16 +57,84 @@ class FromPnhwcFn(Function):
 # ------------------------------------------------------------------------------------------------------------------
 # convolution family
 # ------------------------------------------------------------------------------------------------------------------
+# Set by Trainer.step: weight / bias gradients of leaf parameters that already own a .grad buffer (views into the flat gradient
+# arena of train.FlatAdam) are accumulated straight into it by the wgrad / channel-sum kernels, and autograd is handed None --
+# no per-parameter zero-filled temporary and no AccumulateGrad add (about 900 launches per step).  Off by default: plain
+# autograd semantics (torch.autograd.grad must not touch .grad).
+ACCUM = {'on': False}
+
+
+class TrainPacks:
+    """Packed B operands (forward and transposed / dgrad layouts) of a module's leaf conv weights.  The first training step packs
+    them one by one and records the packs; after freeze() every forward re-packs all of them with ONE launch (PackPlan)."""
+
+    def __init__(self):
+        self.plan = ops.PackPlan()
+        self.cw = {}
+        self.frozen = False
+
+    def begin(self):
+        if self.frozen:
+            self.plan.run()
+
+    def freeze(self, device):
+        if not self.frozen:
+            self.plan.finalize(device)
+            self.frozen = True
+
+
+def train_packs(mod):
+    ptrs = tuple(p.data_ptr() for p in mod.parameters())
+    ent = getattr(mod, '_train_packs', None)
+    if ent is None or ent[0] != ptrs:
+        ent = (ptrs, TrainPacks())
+        mod._train_packs = ent
+    return ent[1]
+
+
+def freeze_packs(mod):
+    ent = getattr(mod, '_train_packs', None)
+    if ent is not None:
+        ent[1].freeze(next(mod.parameters()).device)
+
+
+_CUR_PACKS = [None]
+
+
 def conv_spec(w_shape, taps, n, hout, wout, cpad_in, s_co, s_ci, s_tap, cout, cin, hp=None, wp=None, out_nchw=False, prec=3, out_scale=1.0):
     return SimpleNamespace(w_shape=tuple(w_shape), taps=list(taps), n=n, hout=hout, wout=wout, hp=hp or hout + 2,
                            wp=wp or wout + 2, cpad_in=cpad_in, s_co=s_co, s_ci=s_ci, s_tap=s_tap, cout=cout, cin=cin,
-                           out_nchw=out_nchw, prec=prec, cpad_out=ops.pad_c(cout), out_scale=float(out_scale))
+                           out_nchw=out_nchw, prec=prec, cpad_out=ops.pad_c(cout), out_scale=float(out_scale), packs=_CUR_PACKS[0])
 
 
-def _conv_forward(x, w, bias, addvec, sp, res=None):
-    m_rows = sp.n * sp.hp * sp.wp if len(sp.taps) > 1 else sp.n * sp.hout * sp.wout
-    cw = ops.ConvWeights(sp.cout, [(sp.cpad_in, len(sp.taps))], x.device, precision=sp.prec, m_rows=m_rows)
-    cw.pack_segment(0, w, sp.cin, sp.s_co, sp.s_ci, sp.s_tap)
+def _packed(w, w_ref, kind, sp, device, cy=None):
+    """ConvWeights holding w as the B operand of the forward conv ('fwd') or, with co / ci swapped, of its dgrad ('dgrad')."""
+    ntaps = len(sp.taps)
+    if kind == 'fwd':
+        cout, seg_c, cin_real, s_co, s_ci = sp.cout, sp.cpad_in, sp.cin, sp.s_co, sp.s_ci
+        m_rows = sp.n * sp.hp * sp.wp if ntaps > 1 else sp.n * sp.hout * sp.wout
+    else:
+        cout, seg_c, cin_real, s_co, s_ci = sp.cpad_in, cy, sp.cout, sp.s_ci, sp.s_co
+        m_rows = sp.n * sp.hp * sp.wp if ntaps > 1 else sp.n * (sp.hp - 2) * (sp.wp - 2)
+    packs = sp.packs
+    cacheable = packs is not None and isinstance(w_ref, torch.nn.Parameter) and w_ref.data_ptr() == w.data_ptr()
+    if cacheable:
+        key = (w.data_ptr(), kind, cout, seg_c, ntaps, cin_real, s_co, s_ci, sp.s_tap, sp.prec, m_rows)
+        cw = packs.cw.get(key)
+        if cw is not None:
+            if not packs.frozen:
+                cw.pack_segment(0, w, cin_real, s_co, s_ci, sp.s_tap)
+            return cw                                     # frozen: packed by packs.begin() of this forward
+    cw = ops.ConvWeights(cout, [(seg_c, ntaps)], device, precision=sp.prec, m_rows=m_rows)
+    cw.pack_segment(0, w, cin_real, s_co, s_ci, sp.s_tap)
+    if cacheable and not packs.frozen:
+        packs.cw[key] = cw
+        packs.plan.add(cw, 0, w.data_ptr(), cin_real, s_co, s_ci, sp.s_tap, False)
+    return cw
+
+
+def _conv_forward(x, w, bias, addvec, sp, res=None, w_ref=None):
+    cw = _packed(w, w_ref, 'fwd', sp, x.device)
     if sp.out_nchw:
         out = torch.zeros(sp.n, sp.cout, sp.hout, sp.wout, device=x.device)
         mode, out_c = ops.OUT_NCHW, 0
@@ -74,8 +142,8 @@ def _conv_forward(x, w, bias, addvec, sp, res=None):
         out = ops.alloc_pnhwc(sp.n, sp.hout, sp.wout, sp.cpad_out, x.device, full=(sp.cout != sp.cpad_out))
         mode, out_c = ops.OUT_PNHWC, sp.cpad_out
     ops.conv2d_fused(cw, [ops.conv_src(x, sp.cpad_in, sp.taps)], sp.n, sp.hout, sp.wout, out, out_mode=mode, out_c=out_c,
-                     hp=sp.hp, wp=sp.wp, bias=bias, addvec=addvec, addvec_stride=(addvec.shape[1] if addvec is not None else 0),
-                     res=res, out_scale=sp.out_scale)
+                     hp=sp.hp, wp=sp.wp, bias=bias, addvec=(addvec[0] if addvec is not None else None),
+                     addvec_stride=(addvec[1] if addvec is not None else 0), res=res, out_scale=sp.out_scale)
     return out
 
 
@@ -90,6 +158,19 @@ def _crop(t, hp, wp):
     return t if (t.shape[1] == hp and t.shape[2] == wp) else t[:, :hp, :wp, :].contiguous()
 
 
+def _grad_target(p):
+    """The .grad buffer a kernel may accumulate into directly, or None."""
+    if ACCUM['on'] and not torch.is_grad_enabled() and isinstance(p, torch.nn.Parameter) and p.grad is not None \
+            and p.grad.is_contiguous() and p.requires_grad:
+        return p.grad
+    return None
+
+
+def _wgrad_into(dw, x, dye, sp):
+    ops.conv_wgrad(x, dye, dw, sp.n, sp.hp, sp.wp, sp.cout, sp.cin, sp.cpad_in, sp.taps, sp.s_co, sp.s_ci, sp.s_tap,
+                   precision=sp.prec, gain=sp.out_scale)
+
+
 class ConvFn(Function):
     """y = sp.out_scale * (conv(x; w) + bias + addvec[n, c] + res)   (x, y, res PNHWC; y NCHW when sp.out_nchw).
     The scale and the residual ride in the conv epilogue (layerspp.py:307-309 "(x + h) / sqrt(2)"); in the backward the scale is
@@ -98,12 +179,19 @@ class ConvFn(Function):
     @staticmethod
     def forward(ctx, x, w, bias, addvec, res, sp):
         x = x.contiguous()
+        ctx.w_ref, ctx.b_ref = w, bias
         w = w.contiguous()
         ctx.sp = sp
         ctx.has_bias, ctx.has_addvec, ctx.has_res = bias is not None, addvec is not None, res is not None
         ctx.save_for_backward(x, w)
-        return _conv_forward(x, w, bias, addvec.contiguous() if addvec is not None else None, sp,
-                             res.contiguous() if res is not None else None)
+        av = getattr(sp, 'av', None)      # (hub, column offset): addvec is the wide hub tensor, this conv reads / differentiates a slice
+        if av is not None:
+            assert addvec.stride(1) == 1
+            addvec = (addvec.data_ptr() + 4 * av[1], addvec.stride(0))
+        elif addvec is not None:
+            addvec = addvec.contiguous()
+            addvec = (addvec, addvec.shape[1])
+        return _conv_forward(x, w, bias, addvec, sp, res.contiguous() if res is not None else None, w_ref=ctx.w_ref)
 
     @staticmethod
     def backward(ctx, dy):
@@ -112,21 +200,33 @@ class ConvFn(Function):
         if sp.out_nchw:
             dy = ToPnhwcFn.apply(dy, sp.cpad_out)
         dyc = dy.contiguous()
-        dx = DgradFn.apply(dyc, w, sp) if ctx.needs_input_grad[0] else None
-        dw = WgradFn.apply(x, dyc, sp) if ctx.needs_input_grad[1] else None
+        dx = DgradFn.apply(dyc, w, sp, ctx.w_ref) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            tgt = _grad_target(ctx.w_ref)
+            if tgt is not None and not dyc.requires_grad:
+                _wgrad_into(tgt, x, _embed(dyc, sp.hp, sp.wp).contiguous(), sp)
+            else:
+                dw = WgradFn.apply(x, dyc, sp)
         need_db = ctx.has_bias and ctx.needs_input_grad[2]
         need_dav = ctx.has_addvec and ctx.needs_input_grad[3]
         db = dav = dres = None
         if need_db or need_dav:
             if torch.is_grad_enabled() and dyc.requires_grad:
                 # create_graph pass: keep the reductions differentiable
+                assert getattr(sp, 'av', None) is None, 'hub-mode addvec is first-order only (generator)'
                 db = dyc.sum(dim=(0, 1, 2))[:sp.cout] * sp.out_scale if need_db else None
                 dav = dyc.sum(dim=(1, 2))[:, :sp.cout] * sp.out_scale if need_dav else None
             else:
-                # one streaming pass of the PNHWC reduction kernel gives the per-(sample, channel) sums both gradients need
-                nc = ops.stats_fwd(dyc)[:, :sp.cout, 0] * sp.out_scale
-                dav = nc.float() if need_dav else None
-                db = nc.sum(0).float() if need_db else None
+                # one pass over dy gives the per-(sample, channel) sums (Dense_0 gradient) and the bias gradient, the latter
+                # accumulated straight into bias.grad when that is allowed
+                btgt = _grad_target(ctx.b_ref) if need_db else None
+                av = getattr(sp, 'av', None)
+                into = None
+                if need_dav and av is not None:
+                    into = (av[0].buf.data_ptr() + 4 * av[1], av[0].buf.stride(0))
+                dav, db = ops.channel_grads(dyc, sp.cout, sp.out_scale, need_dav=need_dav, db_accum=btgt,
+                                            need_db=need_db and btgt is None, dav_into=into)
         if ctx.has_res and ctx.needs_input_grad[4]:
             dres = dyc * sp.out_scale if sp.out_scale != 1.0 else dyc
         return dx, dw, db, dav, dres, None
@@ -136,17 +236,16 @@ class DgradFn(Function):
     """dx[q] = sum_t W_t^T dy[q - off_t]: the same implicit-GEMM kernel with adjoint taps and the transposed operand."""
 
     @staticmethod
-    def forward(ctx, dy, w, sp):
+    def forward(ctx, dy, w, sp, w_ref=None):
         ctx.sp = sp
+        ctx.w_ref = w_ref
         dy = dy.contiguous()
         w = w.contiguous()
         ctx.save_for_backward(dy, w)
         # output space = the conv's input space (hp x wp padded); dy is embedded into it when the spaces differ (2x2-tap conv)
         dye = _embed(dy, sp.hp, sp.wp).contiguous()
         cy = dye.shape[-1]
-        m_rows = sp.n * sp.hp * sp.wp if len(sp.taps) > 1 else sp.n * (sp.hp - 2) * (sp.wp - 2)
-        cw = ops.ConvWeights(sp.cpad_in, [(cy, len(sp.taps))], dy.device, precision=sp.prec, m_rows=m_rows)
-        cw.pack_segment(0, w, sp.cout, sp.s_ci, sp.s_co, sp.s_tap)   # roles of co / ci swapped
+        cw = _packed(w, w_ref, 'dgrad', sp, dy.device, cy=cy)
         dx = ops.alloc_pnhwc(sp.n, sp.hp - 2, sp.wp - 2, sp.cpad_in, dy.device, full=False)
         taps = [(-dr, -ds) for dr, ds in sp.taps]
         ops.conv2d_fused(cw, [ops.conv_src(dye, cy, taps)], sp.n, sp.hp - 2, sp.wp - 2, dx, out_scale=sp.out_scale)
@@ -162,10 +261,14 @@ class DgradFn(Function):
         g_dy = g_w = None
         if ctx.needs_input_grad[0]:
             spf = SimpleNamespace(**{**vars(sp), 'out_nchw': False})
-            g_dy = ConvFn.apply(ggx, w, None, None, None, spf)
+            g_dy = ConvFn.apply(ggx, ctx.w_ref if ctx.w_ref is not None else w, None, None, None, spf)
         if ctx.needs_input_grad[1]:
-            g_w = WgradFn.apply(ggx, dy, sp)
-        return g_dy, g_w, None
+            tgt = _grad_target(ctx.w_ref)
+            if tgt is not None and not ggx.requires_grad:
+                _wgrad_into(tgt, ggx, _embed(dy, sp.hp, sp.wp).contiguous(), sp)
+            else:
+                g_w = WgradFn.apply(ggx, dy, sp)
+        return g_dy, g_w, None, None
 
 
 class WgradFn(Function):
@@ -179,8 +282,7 @@ class WgradFn(Function):
         ctx.save_for_backward(x, dy)
         dye = _embed(dy, sp.hp, sp.wp).contiguous()
         dw = torch.zeros(sp.w_shape, device=x.device)
-        ops.conv_wgrad(x, dye, dw, sp.n, sp.hp, sp.wp, sp.cout, sp.cin, sp.cpad_in, sp.taps, sp.s_co, sp.s_ci, sp.s_tap,
-                       precision=sp.prec, gain=sp.out_scale)
+        _wgrad_into(dw, x, dye, sp)
         return dw
 
     @staticmethod
@@ -190,7 +292,7 @@ class WgradFn(Function):
         gdw = gdw.contiguous()
         g_x = g_dy = None
         if ctx.needs_input_grad[0]:
-            g_x = DgradFn.apply(dy, gdw, sp)
+            g_x = DgradFn.apply(dy, gdw, sp, None)
         if ctx.needs_input_grad[1]:
             spf = SimpleNamespace(**{**vars(sp), 'out_nchw': False})
             g_dy = _crop(ConvFn.apply(x, gdw, None, None, None, spf), dy.shape[1], dy.shape[2])
@@ -210,17 +312,20 @@ def _pad_cout(w, b, out_nchw=False):
     return w, b
 
 
-def conv3x3(x, w, b, n, h, wd, addvec=None, out_nchw=False, prec=3, res=None, out_scale=1.0):
-    """nn.Conv2d(k=3, s=1, p=1) on PNHWC; w [Cout, Cin, 3, 3] (zero-padded along Cin to x's channel count if needed)."""
+def conv3x3(x, w, b, n, h, wd, addvec=None, out_nchw=False, prec=3, res=None, out_scale=1.0, av=None):
+    """nn.Conv2d(k=3, s=1, p=1) on PNHWC; w [Cout, Cin, 3, 3] (zero-padded along Cin to x's channel count if needed).
+    addvec: [N, Cout] per-sample add, or -- with av = (hub, column offset) -- the wide GradHub tensor holding it as a slice."""
     cout_real = w.shape[0]
     w, b = _pad_cout(w, b, out_nchw)
     if addvec is not None and w.shape[0] != cout_real:
+        assert av is None
         addvec = F.pad(addvec, (0, w.shape[0] - cout_real))
     cout, cin = w.shape[0], w.shape[1]
     cp = x.shape[-1]
     if cin < cp:
         w = F.pad(w, (0, 0, 0, 0, 0, cp - cin))
     sp = conv_spec(w.shape, ops.TAPS_3X3, n, h, wd, cp, cp * 9, 9, 1, cout, cp, out_nchw=out_nchw, prec=prec, out_scale=out_scale)
+    sp.av = av
     return ConvFn.apply(x, w, b, addvec, res, sp)
 
 
@@ -229,11 +334,11 @@ def conv1x1(x, w, b, n, h, wd, prec=3, res=None, out_scale=1.0):
     w, b = _pad_cout(w, b)
     cout, cin = w.shape[0], w.shape[1]
     cp = x.shape[-1]
-    w2 = w.reshape(cout, cin)
     if cin < cp:
-        w2 = F.pad(w2, (0, cp - cin))
-    sp = conv_spec(w2.shape, ops.TAPS_1X1, n, h, wd, cp, cp, 1, 0, cout, cp, prec=prec, out_scale=out_scale)
-    return ConvFn.apply(x, w2, b, None, res, sp)
+        w = F.pad(w.reshape(cout, cin), (0, cp - cin))
+    # a [Cout, Cin, 1, 1] leaf is passed as it is (same memory as [Cout, Cin]): its .grad can then be accumulated in place
+    sp = conv_spec(w.shape, ops.TAPS_1X1, n, h, wd, cp, cp, 1, 0, cout, cp, prec=prec, out_scale=out_scale)
+    return ConvFn.apply(x, w, b, None, res, sp)
 
 
 def nin(x, W, b, n, h, wd, prec=3, res=None, out_scale=1.0):
@@ -353,6 +458,134 @@ def group_norm_act(x, h, w, groups, gamma, beta, act, eps=1e-6):
     return AffineActFn.apply(x, scale, shift, act)
 
 
+class GradHub(Function):
+    """Identity on a wide [N, J] tensor whose consumers each read one column slice (the batched AdaGN style projections and the
+    batched Dense_0 projections).  Instead of J/slice SliceBackward nodes (a zero-filled [N, J] temporary, a copy and an add
+    each: ~250 launches per step) the consumers write their slice of the gradient straight into `hub.buf` in their own backward
+    and hand autograd None; this node returns the assembled buffer once all of them have run."""
+
+    @staticmethod
+    def forward(ctx, x, hub):
+        ctx.set_materialize_grads(False)
+        hub.buf = torch.zeros_like(x)
+        ctx.hub = hub
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        buf = ctx.hub.buf
+        return (buf if g is None else buf + g), None
+
+
+class _Arena:
+    """Zeroed float64 scratch for the per-(sample, channel) statistics of one forward (+ the first-pass sums of its backward):
+    one fill per forward instead of two per GroupNorm.  Capacity is learned from the previous forward of the module."""
+
+    def __init__(self, cap, device):
+        self.buf = torch.zeros(cap, dtype=torch.float64, device=device) if cap > 0 else None
+        self.cap, self.used, self.want = cap, 0, 0
+
+    def take(self, n, device):
+        self.want += n
+        if self.used + n <= self.cap:
+            v = self.buf[self.used:self.used + n]
+            self.used += n
+            return v
+        return torch.zeros(n, dtype=torch.float64, device=device)
+
+
+_CUR_ARENA = [None]
+
+
+def _begin_arena(mod, device):
+    ar = _Arena(getattr(mod, '_arena_cap', 0), device)
+    _CUR_ARENA[0] = ar
+    return ar
+
+
+def _end_arena(mod, ar):
+    mod._arena_cap = max(getattr(mod, '_arena_cap', 0), 2 * ar.want)    # forward statistics + as many backward sums
+    _CUR_ARENA[0] = None
+
+
+class GnActFn(Function):
+    """y = act(gamma[n,c] * GroupNorm(x) + beta[n,c]) on PNHWC as one autograd node (layerspp.py:46-63 + the SiLU of :279,300).
+    forward : per-(n,c) sums -> scale/shift (ddg_gn_prepare) -> apply;  3 launches
+    backward: first-pass sums -> d(gamma), d(beta), statistics coefficients (ddg_gn_bwd_coeffs) -> dx in one pass;  3 launches
+    (was: 3 + 5 kernels, three full-size temporaries and their border clears, fp64 -> fp32 casts).
+    g: SimpleNamespace(groups, hw, eps, act, per_sample, off, c, hub, arena): with per_sample the affine parameters are columns
+    [off, off+c) / [off+c, off+2c) of the wide style tensor `gsrc` and their gradient goes to hub.buf; else gsrc / bsrc are the
+    [C] affine parameters of a plain GroupNorm."""
+
+    @staticmethod
+    def forward(ctx, x, gsrc, bsrc, g):
+        x = x.contiguous()
+        n, c = x.shape[0], x.shape[-1]
+        dev = x.device
+        ar = g.arena
+        st = (ar.take(n * c * 2, dev) if ar is not None else torch.zeros(n * c * 2, dtype=torch.float64, device=dev))
+        ops.stats_fwd(x, out=st)
+        if g.per_sample:
+            assert gsrc.stride(1) == 1
+            gb_stride = gsrc.stride(0)
+            gptr, bptr = gsrc.data_ptr() + 4 * g.off, gsrc.data_ptr() + 4 * (g.off + c)
+        else:
+            gb_stride = 0
+            gptr, bptr = gsrc.contiguous().data_ptr(), bsrc.contiguous().data_ptr()
+        scale = torch.empty(n, c, device=dev, dtype=torch.float32)
+        shift = torch.empty(n, c, device=dev, dtype=torch.float32)
+        ops.gn_prepare(st, c, None, 0, gptr, bptr, gb_stride, g.per_sample, n, g.hw, g.groups, scale, shift, g.eps)
+        ctx.g = g
+        ctx.gb = (gb_stride, g.off)
+        ctx.save_for_backward(x, scale, shift, st, gsrc, bsrc)
+        return ops.affine_act_fwd(x, scale, shift, g.act)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        x, scale, shift, st, gsrc, bsrc = ctx.saved_tensors
+        g = ctx.g
+        n, c = x.shape[0], x.shape[-1]
+        dev = x.device
+        dy = dy.contiguous()
+        ar = g.arena
+        fresh = ar is not None and not getattr(ctx, 'ran', False)
+        sums = ar.take(n * c * 2, dev) if fresh else torch.zeros(n * c * 2, dtype=torch.float64, device=dev)
+        ctx.ran = True
+        ops.affine_act_bwd(x, dy, scale, shift, g.act, need_dx=False, sums=sums)
+        g12 = torch.empty(n, c, 2, device=dev, dtype=torch.float32)
+        gb_stride, off = ctx.gb
+        if g.per_sample:
+            gptr = gsrc.data_ptr() + 4 * off
+            if g.hub is not None:
+                base = g.hub.buf.data_ptr()
+                ops.gn_bwd_coeffs(st, sums, gptr, gb_stride, True, g12, base + 4 * off, base + 4 * (off + c), g.hub.buf.stride(0), n, c,
+                                  g.hw, g.groups, g.eps)
+                d_g = d_b = None
+            else:
+                d_g = torch.zeros_like(gsrc)
+                ops.gn_bwd_coeffs(st, sums, gptr, gb_stride, True, g12, d_g.data_ptr() + 4 * off, d_g.data_ptr() + 4 * (off + c),
+                                  d_g.stride(0), n, c, g.hw, g.groups, g.eps)
+                d_b = None
+        else:
+            dga = torch.empty(n, c, device=dev, dtype=torch.float32)
+            dbe = torch.empty(n, c, device=dev, dtype=torch.float32)
+            ops.gn_bwd_coeffs(st, sums, gsrc.contiguous(), 0, False, g12, dga, dbe, c, n, c, g.hw, g.groups, g.eps)
+            d_g, d_b = dga.sum(0), dbe.sum(0)
+        dx = ops.gn_bwd_dx(x, dy, scale, shift, g12, g.act)
+        return dx, d_g, d_b, None
+
+
+def gn_act(x, h, w, groups, act, gamma=None, beta=None, style=None, off=0, hub=None, eps=1e-6):
+    """Fused GroupNorm (+ AdaGN affine) + activation.  Either gamma / beta ([C] parameters) or style = the wide [N, J] projection
+    tensor with this norm's [gamma | beta] at columns [off, off + 2C)."""
+    g = SimpleNamespace(groups=groups, hw=h * w, eps=eps, act=act, per_sample=style is not None, off=off, c=x.shape[-1], hub=hub,
+                        arena=_CUR_ARENA[0])
+    if style is not None:
+        return GnActFn.apply(x, style, None, g)
+    return GnActFn.apply(x, gamma, beta, g)
+
+
 def _tc_linear(n, k, j):
     """Large projections (the batched AdaGN style / Dense_0 GEMMs) go to the tcgen05 kernels; small ones stay on the SIMT kernel."""
     return j >= 1024 and k % 32 == 0 and n % 8 == 0 and j % 32 == 0
@@ -406,6 +639,32 @@ def _interior(x):
     return x[:, 1:-1, 1:-1, :]
 
 
+class S2dWeightFn(Function):
+    """wt [Cout, Cin, 3, 3] -> w2[co, py, px, ci, dy, dx] = wt[co, ci, 2dy+py, 2dx+px] (zero elsewhere); linear, so the backward
+    is the adjoint gather and the double backward the forward again."""
+
+    @staticmethod
+    def forward(ctx, wt, cp):
+        ctx.dims = (wt.shape[0], wt.shape[1], cp)
+        return ops.s2d_weights(wt, wt.shape[0], wt.shape[1], cp)
+
+    @staticmethod
+    def backward(ctx, g):
+        cout, cin, cp = ctx.dims
+        return S2dWeightAdjFn.apply(g, cout, cin, cp), None
+
+
+class S2dWeightAdjFn(Function):
+    @staticmethod
+    def forward(ctx, g, cout, cin, cp):
+        ctx.cp = cp
+        return ops.s2d_weights(g, cout, cin, cp, adjoint=True)
+
+    @staticmethod
+    def backward(ctx, gg):
+        return S2dWeightFn.apply(gg, ctx.cp), None, None, None
+
+
 def conv_downsample_pnhwc(x, wt, bias, n, h, w, prec=3, res=None, out_scale=1.0):
     """up_or_down_sampling.py:226-262 conv_downsample_2d with k = [1,3,3,1], factor 2 on a PNHWC tensor: pad(2,2) FIR written
     space-to-depth (FirFn mode 3), then the stride-2 3x3 conv as a stride-1 2x2-tap conv over the 4*C s2d channels.
@@ -415,14 +674,7 @@ def conv_downsample_pnhwc(x, wt, bias, n, h, w, prec=3, res=None, out_scale=1.0)
     s2d = FirFn.apply(x, 3, 1.0, 0)                           # [N, ho+3, wo+3, 4*cp]
     wt, bias = _pad_cout(wt, bias)
     cout, cin = wt.shape[0], wt.shape[1]
-    w2 = wt.new_zeros(cout, 2, 2, cp, 2, 2)
-    for dy in range(2):
-        for dx in range(2):
-            for py in range(2):
-                for px in range(2):
-                    r, s_ = 2 * dy + py, 2 * dx + px
-                    if r < 3 and s_ < 3:
-                        w2[:, py, px, :cin, dy, dx] = wt[:, :, r, s_]
+    w2 = S2dWeightFn.apply(wt, cp)                            # [Cout, 2, 2, cp, 2, 2]
     w2 = w2.reshape(cout, 4 * cp, 4)
     sp = conv_spec(w2.shape, ops.TAPS_2X2, n, ho, wo, 4 * cp, 4 * cp * 4, 4, 1, cout, 4 * cp, hp=ho + 3, wp=wo + 3, prec=prec,
                    out_scale=out_scale)
@@ -444,6 +696,9 @@ def generator_forward(mod, x, time_cond, z):
     prec = mod.precision
     N, S = x.shape[0], cfg.image_size
     nf = cfg.num_channels_dae
+    packs = train_packs(mod)
+    packs.begin()
+    _CUR_PACKS[0] = packs
     drop = float(cfg.dropout) if mod.training else 0.0
 
     # z mapping and time embedding
@@ -470,11 +725,14 @@ def generator_forward(mod, x, time_cond, z):
     o = 0
     for k in dense_names:
         dense_off[k] = o; o += P[k + '.weight'].shape[0]
+    style_hub, dense_hub = SimpleNamespace(buf=None), SimpleNamespace(buf=None)
+    style_all = GradHub.apply(style_all, style_hub)
+    dense_all = GradHub.apply(dense_all, dense_hub)
+    arena = _begin_arena(mod, x.device)
 
     def adagn(t, h, w, prefix, act=ops.ACT_SILU):
         c = t.shape[-1]
-        o_ = style_off[prefix + '.style']
-        return group_norm_act(t, h, w, _groups(c), style_all[:, o_:o_ + c], style_all[:, o_ + c:o_ + 2 * c], act)
+        return gn_act(t, h, w, _groups(c), act, style=style_all, off=style_off[prefix + '.style'], hub=style_hub)
 
     def resblock(m, t, h, w):
         pn = f"all_modules.{m['idx']}."
@@ -485,8 +743,8 @@ def generator_forward(mod, x, time_cond, z):
             hh, xs, h, w = fir_up(hh), fir_up(xs), 2 * h, 2 * w
         elif m['down']:
             hh, xs, h, w = fir_down(hh), fir_down(xs), h // 2, w // 2
-        dense = dense_all[:, dense_off[pn + 'Dense_0']:dense_off[pn + 'Dense_0'] + cout]
-        hh = conv3x3(hh, P[pn + 'Conv_0.weight'], P[pn + 'Conv_0.bias'], N, h, w, addvec=dense, prec=prec)
+        hh = conv3x3(hh, P[pn + 'Conv_0.weight'], P[pn + 'Conv_0.bias'], N, h, w, addvec=dense_all, prec=prec,
+                     av=(dense_hub, dense_off[pn + 'Dense_0']))
         hh = adagn(hh, h, w, pn + 'GroupNorm_1')
         if drop > 0:
             hh = F.dropout(hh, drop, True)
@@ -500,7 +758,7 @@ def generator_forward(mod, x, time_cond, z):
     def attn(m, t, h, w):
         pn = f"all_modules.{m['idx']}."
         c = t.shape[-1]
-        g = group_norm_act(t, h, w, _groups(c), P[pn + 'GroupNorm_0.weight'], P[pn + 'GroupNorm_0.bias'], ops.ACT_NONE)
+        g = gn_act(t, h, w, _groups(c), ops.ACT_NONE, gamma=P[pn + 'GroupNorm_0.weight'], beta=P[pn + 'GroupNorm_0.bias'])
         q = _interior(nin(g, P[pn + 'NIN_0.W'], P[pn + 'NIN_0.b'], N, h, w, prec)).reshape(N, h * w, c)
         k = _interior(nin(g, P[pn + 'NIN_1.W'], P[pn + 'NIN_1.b'], N, h, w, prec)).reshape(N, h * w, c)
         v = _interior(nin(g, P[pn + 'NIN_2.W'], P[pn + 'NIN_2.b'], N, h, w, prec)).reshape(N, h * w, c)
@@ -556,9 +814,11 @@ def generator_forward(mod, x, time_cond, z):
             h, cur, _ = resblock(rest[i], h, cur, cur); i += 1
     assert not hs
     g, c = rest[i], rest[i + 1]
-    h = group_norm_act(h, cur, cur, _groups(h.shape[-1]), P[f"all_modules.{g['idx']}.weight"], P[f"all_modules.{g['idx']}.bias"],
-                       ops.ACT_SILU)
+    h = gn_act(h, cur, cur, _groups(h.shape[-1]), ops.ACT_SILU, gamma=P[f"all_modules.{g['idx']}.weight"],
+               beta=P[f"all_modules.{g['idx']}.bias"])
+    _end_arena(mod, arena)
     y = conv3x3(h, P[f"all_modules.{c['idx']}.weight"], P[f"all_modules.{c['idx']}.bias"], N, cur, cur, out_nchw=True, prec=prec)
+    _CUR_PACKS[0] = None
     return y if cfg.not_use_tanh else torch.tanh(y)
 
 
@@ -572,6 +832,9 @@ def discriminator_forward(mod, x, t, x_t):
     P = dict(mod.named_parameters())
     prec = mod.precision
     N, S = x.shape[0], x.shape[-1]
+    packs = train_packs(mod)
+    packs.begin()
+    _CUR_PACKS[0] = packs
     te = ops.timestep_embedding(t, mod.t_emb_dim)
     te = LinearFn.apply(te, P['t_embed.main.0.weight'], P['t_embed.main.0.bias'])
     te = LinearFn.apply(F.leaky_relu(te, 0.2), P['t_embed.main.2.weight'], P['t_embed.main.2.bias'])
@@ -602,4 +865,5 @@ def discriminator_forward(mod, x, t, x_t):
     hcat = torch.cat([h, extra], dim=-1)
     f = conv3x3(hcat, P['final_conv.weight'], P['final_conv.bias'], N, cur, cur, prec=prec)
     f = F.leaky_relu(_interior(f), 0.2).sum(dim=(1, 2))            # [N, C]
+    _CUR_PACKS[0] = None
     return LinearFn.apply(f, P['end_linear.weight'], P['end_linear.bias'])

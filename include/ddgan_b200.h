@@ -171,6 +171,17 @@ long ddg_conv_packed_bytes(int cout, int total_stages, int kb, int precision, in
 int ddg_conv_pack_weights(const float* w, void* out, int cout, int cin_real, int cin_pad, int ntaps, long s_co, long s_ci,
                           long s_tap, int flip_taps, int kb, int stage_offset, int total_stages, int precision, int nt, int batch,
                           long w_batch_stride, cudaStream_t stream);
+/* The same packing for MANY operands in one launch: `items_dev` is a device-resident table (built once per network: the
+ * weights live at fixed addresses), item i covering chunks [chunk_begin, chunk_begin + ddg_conv_pack_chunks(...)) of the
+ * launch; total_chunks = the sum.  Per-item fields mean what the ddg_conv_pack_weights arguments mean (batch = 1). */
+typedef struct {
+  const float* w; void* out;
+  long s_co, s_ci, s_tap;
+  long chunk_begin;
+  int cout, cin_real, cin_pad, ntaps, flip_taps, kb, stage_offset, total_stages, precision, nt;
+} ddg_pack_item;
+long ddg_conv_pack_chunks(int cout, int cin_pad, int ntaps, int kb, int nt);
+int ddg_conv_pack_batch(const ddg_pack_item* items_dev, int n_items, long total_chunks, cudaStream_t stream);
 int ddg_conv2d_fwd(const ddg_conv_desc* desc, cudaStream_t stream);
 /* diagnostics: which kernel variant the last ddg_conv2d_fwd call on this host thread launched (tests assert on it) */
 int ddg_conv_last_launch_info(int* msub, int* nt, int* persistent, int* grid_ctas);
@@ -201,10 +212,32 @@ int ddg_affine_act_fwd(const float* x, const float* scale, const float* shift, f
 /* dx = dy * act'(u) * scale, sums[n][c] = {sum dy*act'(u)*x, sum dy*act'(u)} (float64, accumulated: zero it first) */
 int ddg_affine_act_bwd(const float* x, const float* dy, const float* scale, const float* shift, float* dx, double* sums, int N,
                        int H, int W, int C, int act, cudaStream_t stream);
+/* GroupNorm backward in two passes over the activation (layerspp.py:46-63 under autograd in the reference):
+ *   pass 1 = ddg_affine_act_bwd with dx = NULL: sums[n][c] = {sum gg*x, sum gg}, gg = dy * act'(scale*x + shift)
+ *   ddg_gn_bwd_coeffs: from the forward statistics and those sums, d(gamma), d(beta) per (n, c) (written with row pitch
+ *            dgb_stride, e.g. straight into a slice of the batched style-projection gradient) and g12[n][c] = {d(sum x), d(sum x^2)}
+ *   pass 2 = ddg_gn_bwd_dx: dx = gg * scale + g12[n][c][0] + 2 * x * g12[n][c][1]. */
+int ddg_gn_bwd_coeffs(const double* stats, const double* sums, const float* gamma, int gb_stride, int per_sample, float* g12,
+                      float* dgamma, float* dbeta, int dgb_stride, int N, int C, int HW, int G, float eps, cudaStream_t stream);
+int ddg_gn_bwd_dx(const float* x, const float* dy, const float* scale, const float* shift, const float* g12, float* dx, int N, int H,
+                  int W, int C, int act, cudaStream_t stream);
 /* stats[n][c] = {sum x, sum x^2} over the interior (float64, accumulated: zero it first) */
 int ddg_stats_fwd(const float* x, double* stats, int N, int H, int W, int C, cudaStream_t stream);
 /* dx = g1[n][c] + 2 * x * g2[n][c] on the interior, g = [N][C][2] float32 */
 int ddg_stats_bwd(const float* x, const float* g, float* dx, int N, int H, int W, int C, cudaStream_t stream);
+
+/* Bias and per-(sample, channel) gradients of a conv from its PNHWC output gradient dy [N][H+2][W+2][C] (C % 32 == 0):
+ *   dav[n*dav_stride + c] = scale * sum_{h,w} dy[n][h][w][c]   (written; when ddg_channel_grads_splits(...) > 1 it is
+ *                                                                accumulated instead and must be zeroed by the caller)
+ *   db[c]               += scale * sum_{n,h,w} dy[n][h][w][c]   (accumulated: bias.grad or a zeroed buffer)
+ * for c < cout; either output may be NULL.  The gradients of layerspp.py:298-299 (Dense_0) and of every conv bias. */
+int ddg_channel_grads_splits(int N, int H, int W, int C);
+int ddg_channel_grads(const float* dy, float* dav, float* db, int N, int H, int W, int C, int cout, float scale, int dav_stride,
+                      cudaStream_t stream);
+/* conv_downsample_2d weights (up_or_down_sampling.py:149-183): wt [Cout][Cin][3][3] -> w2 [Cout][2][2][cp][2][2] with
+ * w2[co][py][px][ci][dy][dx] = wt[co][ci][2dy+py][2dx+px] (zero outside the 3x3 support / ci >= Cin): the stride-2 conv after the
+ * pad-(2,2) FIR as a stride-1 2x2-tap conv over space-to-depth channels.  adjoint=1: src = d(w2), dst = d(wt). */
+int ddg_s2d_weights(const float* src, float* dst, int Cout, int Cin, int cp, int adjoint, cudaStream_t stream);
 
 /* ---- flat-arena optimiser pass (ddgan.py:484-485, 507-508 clip_grad_norm_ + Adam; ema.py:45-55) --------------------------
  * out[0] = sum of squares of the gradient arena (float64; zeroed by the call). */

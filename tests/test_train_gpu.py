@@ -86,6 +86,28 @@ def test_groupnorm_fir_linear_grads():
     g = torch.autograd.grad((yo * gy.to(DEV)).sum(), (xd, gd, bd))
     for a, b_ in zip(g, g_ref):
         assert O.rel_l2(a.cpu(), b_) < 5e-5
+    # the fused node the generator's training path uses (GnActFn: 3 + 3 launches), AdaGN form: [gamma | beta] are columns of a
+    # wider projection tensor; and the shared-affine form of the attention / output norms
+    xd, gd, bd = x.to(DEV).requires_grad_(True), gamma.to(DEV).requires_grad_(True), beta.to(DEV).requires_grad_(True)
+    pad = torch.zeros(n, 8, device=DEV)
+    style = torch.cat([pad, gd, bd, pad], 1)
+    y = TG.gn_act(TG.ToPnhwcFn.apply(xd, c), h, h, O.num_groups(c), ops.ACT_SILU, style=style, off=8)
+    yo = TG.FromPnhwcFn.apply(TG.fir_down(TG.fir_up(y)), c)
+    assert O.rel_l2(yo.detach().cpu(), ref.detach()) < 1e-5
+    g = torch.autograd.grad((yo * gy.to(DEV)).sum(), (xd, gd, bd))
+    for a, b_ in zip(g, g_ref):
+        assert O.rel_l2(a.cpu(), b_) < 5e-5
+    ga, be = 1 + seeded((c,), 16) * 0.2, seeded((c,), 17) * 0.2
+    xr, gr, br = x.clone().requires_grad_(True), ga.clone().requires_grad_(True), be.clone().requires_grad_(True)
+    ref2 = O.group_norm(xr, O.num_groups(c), weight=gr, bias=br)
+    gy2 = seeded(tuple(ref2.shape), 18)
+    g_ref2 = torch.autograd.grad((ref2 * gy2).sum(), (xr, gr, br))
+    xd, gd, bd = x.to(DEV).requires_grad_(True), ga.to(DEV).requires_grad_(True), be.to(DEV).requires_grad_(True)
+    yo = TG.FromPnhwcFn.apply(TG.gn_act(TG.ToPnhwcFn.apply(xd, c), h, h, O.num_groups(c), ops.ACT_NONE, gamma=gd, beta=bd), c)
+    assert O.rel_l2(yo.detach().cpu(), ref2.detach()) < 1e-5
+    g = torch.autograd.grad((yo * gy2.to(DEV)).sum(), (xd, gd, bd))
+    for a, b_ in zip(g, g_ref2):
+        assert O.rel_l2(a.cpu(), b_) < 5e-5
     # linear
     xl = seeded((64, 100), 9); W = seeded((256, 100), 10, 0.1); b = seeded((256,), 11)
     xr, Wr, br = xl.clone().requires_grad_(True), W.clone().requires_grad_(True), b.clone().requires_grad_(True)
