@@ -201,6 +201,7 @@ struct ConvDev {
   int batch_rows;              // >0: batched GEMM mode (gather only): blockIdx.z = batch, rows per batch
   int tiles_m, n_tiles;        // persistent variant: tile = n_tile * tiles_m + m_tile, CTA b runs tiles b, b + grid, ...
   long w_batch_stride;         // bytes between the packed B operands of consecutive batches
+  int nsa;                     // A-operand ring depth (2..4 stages, whatever the shared-memory budget allows)
 };
 
 constexpr int kProdWarps = 8;
@@ -243,8 +244,11 @@ __device__ __forceinline__ void decode_out_row(const ConvDev& p, int m, int m_en
   if (n >= p.N) n = p.N - 1;
 }
 
-template <int MSUB, int NT, int KB, int PREC, bool PERSIST>
+// PROF: per-role cycle counters (clock64 pairs around every barrier wait) are compiled in only for the tuning builds that
+// tools/conv_prof.py asks for through desc.debug_prof; the production instantiations carry none of that.
+template <int MSUB, int NT, int KB, int PREC, bool PERSIST, bool PROF>
 __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvDev p) {
+#define DDG_CLK() (PROF ? clock64() : 0LL)
   using Cfg = ConvCfg<MSUB, NT, KB, PREC>;
   constexpr int ACC_COLS = MSUB * NT;                                   // TMEM columns of one accumulator set
   constexpr int TM_COLS = PERSIST ? 2 * Cfg::TMEM_COLS : Cfg::TMEM_COLS;  // persistent: two sets, epilogue(i) overlaps mainloop(i+1)
@@ -259,12 +263,13 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   const uint32_t bar_base = smem_u32(bars);
   auto fullA = [&](int s) { return bar_base + 8u * s; };
-  auto emptyA = [&](int s) { return bar_base + 8u * (2 + s); };
-  auto fullB = [&](int s) { return bar_base + 8u * (4 + s); };
-  auto emptyB = [&](int s) { return bar_base + 8u * (4 + NSB + s); };
-  auto accFull = [&](int b) { return bar_base + 8u * (4 + 2 * NSB + b); };
-  auto accEmpty = [&](int b) { return bar_base + 8u * (6 + 2 * NSB + b); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (8 + 2 * NSB));
+  auto emptyA = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto fullB = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto emptyB = [&](int s) { return bar_base + 8u * (8 + NSB + s); };
+  auto accFull = [&](int b) { return bar_base + 8u * (8 + 2 * NSB + b); };
+  auto accEmpty = [&](int b) { return bar_base + 8u * (10 + 2 * NSB + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (12 + 2 * NSB));
+  const int NSA = p.nsa;
   uint8_t* sB = smem + 256;
   const int a_plane = KCH * p.win_pitch;          // bytes of one A plane
   const int a_stage = a_plane * NPL;
@@ -296,7 +301,7 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
   };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(fullA(s), kProdWarps); mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(fullA(s), kProdWarps); mbar_init(emptyA(s), 1); }
     for (int s = 0; s < NSB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(accFull(b), 1); mbar_init(accEmpty(b), PERSIST ? 4 : kProdWarps); }
     fence_barrier_init();
@@ -316,9 +321,10 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
   // =================================== epilogue (one tile) ===================================
   // quad: TMEM lane quadrant of the calling warp; the warp handles column chunks half0, half0 + hstep, ...
   // it: tile iteration of this CTA (selects the accumulator set and the barrier parity).
-  auto run_epilogue = [&](int it, int quad, int half0, int hstep, bool release) {
+  // wait_acc = false: the caller has already established that the tile's MMAs completed (see the producers' helper call)
+  auto run_epilogue = [&](int it, int quad, int half0, int hstep, bool release, bool wait_acc) {
     const int ab = PERSIST ? (it & 1) : 0;
-    mbar_wait(accFull(ab), PERSIST ? ((it >> 1) & 1) : 0);
+    if (wait_acc) mbar_wait(accFull(ab), PERSIST ? ((it >> 1) & 1) : 0);
     tc_fence_after();
     constexpr int CW = (NT >= 64) ? 32 : 16;         // columns per tcgen05.ld
     constexpr int NCHUNK = NT / CW;
@@ -566,14 +572,15 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
     };
 
     if (PERSIST) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsProd));
-    uint32_t ga = 0;                                   // A stages produced so far (ring position / parity across tiles)
+    int stA_p = 0; uint32_t phA_p = 0;                  // A ring position / parity (carried across tiles)
+    int last_st = 0; uint32_t last_ph = 0;              // stage / parity of the last K-block this thread produced
     int it = 0;
     bool prof_on = false;
     long long t_prod0 = 0, w_emptyA = 0;
     for (int tile = tile_first; tile < tile_end; tile += tile_stride, ++it) {
       set_tile(tile);
-      prof_on = (p.prof != nullptr) && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0;
-      if (it == 0) t_prod0 = clock64();
+      prof_on = PROF && (p.prof != nullptr) && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0;
+      if (it == 0) t_prod0 = DDG_CLK();
     float cur[IMAX][8], nxt[IMAX][8];
     int off_c[IMAX], nn_c[IMAX], off_n[IMAX], nn_n[IMAX];
     int s_cur = 0, kb_cur = 0;
@@ -638,10 +645,11 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
         }
       }
       // ---- convert + store the current K-block ----
-      const int st = ga & 1;
-      const uint32_t ph = (ga >> 1) & 1;
-      ++ga;
-      { const long long tw = clock64(); mbar_wait(emptyA(st), ph ^ 1); w_emptyA += clock64() - tw; }
+      const int st = stA_p;
+      const uint32_t ph = phA_p;
+      last_st = st; last_ph = ph;
+      if (++stA_p == NSA) { stA_p = 0; phA_p ^= 1u; }
+      { const long long tw = DDG_CLK(); mbar_wait(emptyA(st), ph ^ 1); w_emptyA += DDG_CLK() - tw; }
       uint8_t* dst_hi = sA + st * a_stage + c * p.win_pitch;
       uint8_t* dst_lo = dst_hi + a_plane;
       int row_lo, row_hi;
@@ -679,24 +687,32 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
 
     }
     if (!PERSIST) {
-      const long long t_prod1 = clock64();
+      const long long t_prod1 = DDG_CLK();
       mbar_wait(accFull(0), 0);
-      const long long t_epi0 = clock64();
-      run_epilogue(0, warp & 3, warp >> 2, 2, true);
+      const long long t_epi0 = DDG_CLK();
+      run_epilogue(0, warp & 3, warp >> 2, 2, true, true);
       if (prof_on && tid == 0) {
         p.prof[0] = t_prod1 - t_prod0;   // producer loop total
         p.prof[1] = w_emptyA;            // ... of which waiting for a free A stage
         p.prof[2] = t_epi0 - t_prod1;    // waiting for the accumulator after the last A stage
-        p.prof[3] = clock64() - t_epi0;  // epilogue
+        p.prof[3] = DDG_CLK() - t_epi0;  // epilogue
       }
     }
     // last tile of a persistent CTA: nothing is left to produce, so the producer warps take two thirds of its epilogue
     // (outside the tile loop: the register pipeline of the producer loop is dead here)
     if (PERSIST && prof_on && tid == 0) {
-      p.prof[0] = clock64() - t_prod0;   // producer loops of all tiles of this CTA
+      p.prof[0] = DDG_CLK() - t_prod0;   // producer loops of all tiles of this CTA
       p.prof[1] = w_emptyA;              // ... of which waiting for a free A stage
     }
-    if (PERSIST && it > 0) run_epilogue(it - 1, warp & 3, 1 + (warp >> 2), 3, false);
+    // The producers may run several tiles ahead of the MMA issuer (A ring depth), so they must NOT wait on accFull by parity: a
+    // parity wait is only sound for a waiter at most one phase behind, and two phases early it is satisfied by the previous use of
+    // the same accumulator set (seen as 1e-3 errors on short-K layers with a 4-stage ring).  The empty barrier of the last A stage
+    // they produced is a barrier whose phase they do track: tcgen05.commit fires it when every MMA issued so far -- i.e. the whole
+    // last tile -- has completed, which is exactly the condition for reading the accumulators.
+    if (PERSIST && it > 0) {
+      mbar_wait(emptyA(last_st), last_ph);
+      run_epilogue(it - 1, warp & 3, 1 + (warp >> 2), 3, false, false);
+    }
   } else if (warp < kEpiWarp0) {
     // WG2: the two single-thread roles (+ two idle warps in the persistent layout); their registers go to the producers
     if (PERSIST) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsUtil));
@@ -704,7 +720,7 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
     // =================================== weight loader (TMA bulk) ===================================
     if (lane == 0) {
       long long w_emptyB = 0;
-      const long long t_l0 = clock64();
+      const long long t_l0 = DDG_CLK();
       uint32_t gb = 0;                                 // B stages issued so far (ring position / parity across tiles)
       for (int tile = tile_first; tile < tile_end; tile += tile_stride) {
         set_tile(tile);
@@ -713,13 +729,13 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
         for (int i = 0; i < p.total_stages; ++i, ++gb) {
           const int st = gb % NSB;
           const uint32_t ph = (gb / NSB) & 1;
-          { const long long tw = clock64(); mbar_wait(emptyB(st), ph ^ 1); w_emptyB += clock64() - tw; }
+          { const long long tw = DDG_CLK(); mbar_wait(emptyB(st), ph ^ 1); w_emptyB += DDG_CLK() - tw; }
           mbar_arrive_expect_tx(fullB(st), Cfg::B_STAGE);
           tma_bulk_g2s(smem_u32(sB + st * Cfg::B_STAGE), wsrc + (size_t)i * Cfg::B_STAGE, Cfg::B_STAGE, fullB(st));
         }
       }
-      if (p.prof != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) {
-        p.prof[4] = clock64() - t_l0;  // loader loop total
+      if (PROF && p.prof != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) {
+        p.prof[4] = DDG_CLK() - t_l0;  // loader loop total
         p.prof[5] = w_emptyB;          // ... waiting for a free B stage
       }
     }
@@ -741,27 +757,29 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
       const uint32_t a_kk16 = (2u * (uint32_t)p.win_pitch) >> 4;                      // +16 channels, in 16-byte units
       constexpr uint32_t b_kk16 = (2u * NT * 16u) >> 4;
       const uint32_t a_sub16 = (uint32_t)p.sub_stride >> 4;
-      uint32_t bi = 0, ga = 0;                         // B / A stages consumed so far (ring positions across tiles)
+      uint32_t bi = 0;                                 // B stages consumed so far (ring position across tiles)
+      int stA_m = 0; uint32_t phA_m = 0;               // A ring position / parity
       long long w_fullA = 0, w_fullB = 0, w_accE = 0;
-      const long long t_m0 = clock64();
+      const long long t_m0 = DDG_CLK();
       int it = 0;
       for (int tile = tile_first; tile < tile_end; tile += tile_stride, ++it) {
       const int ab = PERSIST ? (it & 1) : 0;
       const uint32_t tmem_acc = tmem_base + (uint32_t)(ab * ACC_COLS);
       // the epilogue of the tile that used this accumulator set two iterations ago must have drained it
-      { const long long tw = clock64(); mbar_wait(accEmpty(ab), (PERSIST ? ((it >> 1) & 1) : 0) ^ 1); w_accE += clock64() - tw; }
+      { const long long tw = DDG_CLK(); mbar_wait(accEmpty(ab), (PERSIST ? ((it >> 1) & 1) : 0) ^ 1); w_accE += DDG_CLK() - tw; }
       tc_fence_after();
       uint32_t acc = 0;
       int s_m = 0, kb_m = 0;
-      for (int kb_idx = 0; kb_idx < nkb_total; ++kb_idx, ++ga) {
+      for (int kb_idx = 0; kb_idx < nkb_total; ++kb_idx) {
         const SrcDev& S = p.src[s_m];
-        const int stA = ga & 1;
-        { const long long tw = clock64(); mbar_wait(fullA(stA), (ga >> 1) & 1); w_fullA += clock64() - tw; }
+        const int stA = stA_m;
+        { const long long tw = DDG_CLK(); mbar_wait(fullA(stA), phA_m); w_fullA += DDG_CLK() - tw; }
+        if (++stA_m == NSA) { stA_m = 0; phA_m ^= 1u; }
         const uint32_t a_hi_lo = a_lbo_f | ((smem_u32(sA + stA * a_stage) >> 4) & 0x3FFFu);
         const uint32_t a_lo_lo = a_lbo_f | ((smem_u32(sA + stA * a_stage + a_plane) >> 4) & 0x3FFFu);
         for (int t = 0; t < S.ntaps; ++t, ++bi) {
           const int stB = bi % NSB;
-          { const long long tw = clock64(); mbar_wait(fullB(stB), (bi / NSB) & 1); w_fullB += clock64() - tw; }
+          { const long long tw = DDG_CLK(); mbar_wait(fullB(stB), (bi / NSB) & 1); w_fullB += DDG_CLK() - tw; }
           tc_fence_after();
           if (leader) {
             const uint32_t b_hi_lo = b_lbo_f | ((smem_u32(sB + stB * Cfg::B_STAGE) >> 4) & 0x3FFFu);
@@ -798,8 +816,8 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
       __syncwarp();
       }
       if (leader) {
-        if (p.prof != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) {
-          p.prof[6] = clock64() - t_m0;  // MMA issue loop total
+        if (PROF && p.prof != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) {
+          p.prof[6] = DDG_CLK() - t_m0;  // MMA issue loop total
           p.prof[7] = w_fullA;           // ... waiting for A
           p.prof[8] = w_fullB;           // ... waiting for B
           p.prof[9] = w_accE;            // ... waiting for the epilogue to drain an accumulator set (persistent)
@@ -814,15 +832,15 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
     int it = 0;
     long long w_accF = 0;
-    const long long t_e0 = clock64();
+    const long long t_e0 = DDG_CLK();
     for (int tile = tile_first; tile < tile_end; tile += tile_stride, ++it) {
       set_tile(tile);
       const bool last = tile + tile_stride >= tile_end;
-      { const long long tw = clock64(); mbar_wait(accFull(it & 1), (it >> 1) & 1); w_accF += clock64() - tw; }
-      run_epilogue(it, warp & 3, 0, last ? 3 : 1, true);
+      { const long long tw = DDG_CLK(); mbar_wait(accFull(it & 1), (it >> 1) & 1); w_accF += DDG_CLK() - tw; }
+      run_epilogue(it, warp & 3, 0, last ? 3 : 1, true, true);
     }
-    if (p.prof != nullptr && blockIdx.x == gridDim.x / 2 && warp == kEpiWarp0 && lane == 0) {
-      p.prof[11] = clock64() - t_e0;   // epilogue warps: whole tile loop
+    if (PROF && p.prof != nullptr && blockIdx.x == gridDim.x / 2 && warp == kEpiWarp0 && lane == 0) {
+      p.prof[11] = DDG_CLK() - t_e0;   // epilogue warps: whole tile loop
       p.prof[12] = w_accF;             // ... of which waiting for a finished accumulator set
     }
   }
@@ -832,6 +850,7 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
     tc_fence_after();
     tmem_dealloc<TM_COLS>(tmem_base);
   }
+#undef DDG_CLK
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -909,12 +928,23 @@ static int pick_nt(int cout, long m_rows) {
 }
 static bool valid_nt(int nt) { return nt == 16 || nt == 64 || nt == 128 || nt == 256; }
 
-template <int MSUB, int NT, int KB, int PREC, bool PERSIST = false>
+static int g_nsa_max = getenv("DDG_CONV_NSA") ? atoi(getenv("DDG_CONV_NSA")) : 4;
+
+template <int MSUB, int NT, int KB, int PREC, bool PERSIST = false, bool PROF = false>
 static int launch_conv(ConvDev& d, int n_tiles, cudaStream_t stream) {
   using Cfg = ConvCfg<MSUB, NT, KB, PREC>;
-  const size_t smem = 256 + (size_t)Cfg::NSB * Cfg::B_STAGE + 2 * (size_t)Cfg::NPL * Cfg::KCH * d.win_pitch;
-  if (smem > 227 * 1024) { ddg_set_last_error("conv_tc: shared memory budget exceeded"); return DDG_ERR_UNSUPPORTED; }
-  auto kern = conv_tc_kernel<MSUB, NT, KB, PREC, PERSIST>;
+  const size_t a_stage = (size_t)Cfg::NPL * Cfg::KCH * d.win_pitch;
+  const size_t fixed = 256 + (size_t)Cfg::NSB * Cfg::B_STAGE;
+  if (fixed + 2 * a_stage > 227 * 1024) { ddg_set_last_error("conv_tc: shared memory budget exceeded"); return DDG_ERR_UNSUPPORTED; }
+  // A ring: as deep as the budget allows, up to 4 stages (1-tap K segments consume a stage in ~12 MMAs: two stages cannot hide the
+  // load -> convert -> store latency of the producers)
+  int nsa = (int)((227 * 1024 - fixed) / a_stage);
+  nsa = nsa > g_nsa_max ? g_nsa_max : nsa;
+  if (nsa < 2) nsa = 2;
+  if (nsa > 4) nsa = 4;
+  d.nsa = nsa;
+  const size_t smem = fixed + (size_t)nsa * a_stage;
+  auto kern = conv_tc_kernel<MSUB, NT, KB, PREC, PERSIST, PROF>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1094,6 +1124,15 @@ extern "C" int ddg_conv2d_fwd(const ddg_conv_desc* c, cudaStream_t stream) {
   d.win_pitch = rows * 16;
   const int prec = c->precision == 1 ? 1 : 3;
 
+  // tuning builds with cycle counters (tools/conv_prof.py): the three shapes that dominate a generator forward
+  if (d.prof != nullptr && prec == 3) {
+    if (persist && nt == 128 && msub == 2) return launch_conv<2, 128, 32, 3, true, true>(d, n_tiles, stream);
+    if (persist && nt == 256) return launch_conv<1, 256, 32, 3, true, true>(d, n_tiles, stream);
+    if (!persist && nt == 256 && msub == 1) return launch_conv<1, 256, 32, 3, false, true>(d, n_tiles, stream);
+    d.prof = nullptr;   // no counter build of this variant: run the production kernel
+  } else {
+    d.prof = nullptr;
+  }
 #define DDG_LAUNCH_P(MS, NTV, PR) return launch_conv<MS, NTV, 32, PR, true>(d, n_tiles, stream)
   if (persist) {
     if (prec == 3) {

@@ -166,3 +166,32 @@ extern "C" int ddg_s2d_weights(const float* src, float* dst, int Cout, int Cin, 
   DDG_CHECK_LAUNCH();
   return DDG_OK;
 }
+
+// ---- image output (test_ddgan.py:190-201: to_range_0_1 then torchvision.utils.save_image per image) ------------------------------
+// out[n][h][w][c] = (uint8) clamp((x[n][c][h][w] * scale + shift) * 255 + 0.5, 0, 255): the whole batch leaves the device as bytes in
+// the layout image encoders want, instead of N float tensors converted one by one on the host.
+namespace ddg {
+__global__ void __launch_bounds__(256) images_to_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int N, int C, int H,
+                                                          int W, float scale, float shift) {
+  const long total = (long)N * H * W;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long n = i / ((long)H * W);
+    const long p = i - n * (long)H * W;
+    for (int c = 0; c < C; ++c) {
+      float v = (x[(n * C + c) * (long)H * W + p] * scale + shift) * 255.f + 0.5f;
+      v = fminf(fmaxf(v, 0.f), 255.f);
+      out[i * C + c] = (uint8_t)v;
+    }
+  }
+}
+}  // namespace ddg
+
+extern "C" int ddg_images_to_u8(const float* x, uint8_t* out, int N, int C, int H, int W, float scale, float shift, cudaStream_t stream) {
+  if (!x || !out || N < 1 || C < 1) { ddg_set_last_error("images_to_u8: bad args"); return DDG_ERR_ARG; }
+  const long total = (long)N * H * W;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148L * 16) blocks = 148L * 16;
+  ddg::images_to_u8_kernel<<<(int)blocks, 256, 0, stream>>>(x, out, N, C, H, W, scale, shift);
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}

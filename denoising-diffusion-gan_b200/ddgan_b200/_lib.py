@@ -86,6 +86,7 @@ _SIGNATURES = {
     'ddg_channel_grads_splits': ([_I] * 4, _I),
     'ddg_channel_grads': ([_P, _P, _P] + [_I] * 5 + [_F, _I, _P], _I),
     'ddg_s2d_weights': ([_P, _P, _I, _I, _I, _I, _P], _I),
+    'ddg_images_to_u8': ([_P, _P, _I, _I, _I, _I, _F, _F, _P], _I),
     'ddg_conv2d_fwd': ([C.POINTER(ConvDesc), _P], _I),
     'ddg_conv2d_wgrad': ([C.POINTER(WgradDesc), _P], _I),
     'ddg_affine_act_fwd': ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),

@@ -239,6 +239,10 @@ int ddg_channel_grads(const float* dy, float* dav, float* db, int N, int H, int 
  * pad-(2,2) FIR as a stride-1 2x2-tap conv over space-to-depth channels.  adjoint=1: src = d(w2), dst = d(wt). */
 int ddg_s2d_weights(const float* src, float* dst, int Cout, int Cin, int cp, int adjoint, cudaStream_t stream);
 
+/* Image output (test_ddgan.py:190-201): out[n][h][w][c] = (uint8) clamp((x[n][c][h][w]*scale + shift)*255 + 0.5, 0, 255), i.e.
+ * to_range_0_1 (scale = shift = 0.5) followed by torchvision.utils.save_image's quantisation, for the whole NCHW batch at once. */
+int ddg_images_to_u8(const float* x, uint8_t* out, int N, int C, int H, int W, float scale, float shift, cudaStream_t stream);
+
 /* ---- flat-arena optimiser pass (ddgan.py:484-485, 507-508 clip_grad_norm_ + Adam; ema.py:45-55) --------------------------
  * out[0] = sum of squares of the gradient arena (float64; zeroed by the call). */
 int ddg_grad_norm_sq(const float* g, long n, double* out, cudaStream_t stream);
