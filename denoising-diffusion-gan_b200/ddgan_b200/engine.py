@@ -68,6 +68,7 @@ class _EngineBase:
         self.graph = None
         self.n_launches = 0
         self.conv_flops = 0
+        self.conv_bytes = 0      # algorithmic HBM bytes of the conv launches: inputs + packed weights + output (+ residual), once each
 
     def _alloc_stats(self, c):
         n = self.N * c * 2
@@ -99,6 +100,7 @@ class _EngineBase:
         f = sys._getframe(1)
         self._step(lambda d=desc: ops.conv_launch(d), name=f'conv {f.f_code.co_name}:{f.f_lineno} cout={cout} {hout}x{wout} srcs={[(s["C"], len(s["taps"])) for s in srcs]}')
         self.conv_flops += 2 * n * hout * wout * cout * sum(s['C'] * len(s['taps']) for s in srcs)
+        self.conv_bytes += 4 * n * hout * wout * (sum(s['C'] for s in srcs) + cout * (2 if kw.get('res') is not None else 1)) + cw.bytes_per_batch
         return cw
 
     def _linear_rows(self, x, k, w, b, out, act_in=ops.ACT_NONE):

@@ -19,4 +19,4 @@ torch.cuda.cudart().cudaProfilerStart()
 eng.run_steps()
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
-print('done')
+print('done; conv launches:', len([n for n in eng.step_names if n.startswith('conv')]), 'algorithmic conv bytes per forward:', eng.conv_bytes)
