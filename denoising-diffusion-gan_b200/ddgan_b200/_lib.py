@@ -37,6 +37,12 @@ class WgradDesc(C.Structure):
                 ('tap_ds', C.c_int8 * 9), ('s_co', C.c_long), ('s_ci', C.c_long), ('s_tap', C.c_long), ('precision', C.c_int), ('gain', C.c_float), ('debug_prof', C.c_void_p)]
 
 
+class AttnDesc(C.Structure):
+    _fields_ = [('qkv', C.c_void_p), ('w3pack', C.c_void_p), ('bias', C.c_void_p), ('res', C.c_void_p), ('out', C.c_void_p),
+                ('stats', C.c_void_p), ('N', C.c_int), ('H', C.c_int), ('W', C.c_int), ('C', C.c_int), ('out_scale', C.c_float),
+                ('precision', C.c_int)]
+
+
 class PackItem(C.Structure):
     _fields_ = [('w', C.c_void_p), ('out', C.c_void_p), ('s_co', C.c_long), ('s_ci', C.c_long), ('s_tap', C.c_long),
                 ('chunk_begin', C.c_long), ('cout', C.c_int), ('cin_real', C.c_int), ('cin_pad', C.c_int), ('ntaps', C.c_int),
@@ -89,6 +95,7 @@ _SIGNATURES = {
     'ddg_images_to_u8': ([_P, _P, _I, _I, _I, _I, _F, _F, _P], _I),
     'ddg_conv2d_fwd': ([C.POINTER(ConvDesc), _P], _I),
     'ddg_conv2d_wgrad': ([C.POINTER(WgradDesc), _P], _I),
+    'ddg_attention_fwd': ([C.POINTER(AttnDesc), _P], _I),
     'ddg_affine_act_fwd': ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
     'ddg_affine_act_bwd': ([_P] * 6 + [_I] * 5 + [_P], _I),
     'ddg_gn_bwd_coeffs': ([_P, _P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P], _I),

@@ -388,6 +388,18 @@ class GeneratorEngine(_EngineBase):
             cw.pack_nin_weight(0, wqkv)
         self._conv(3 * C, [ops.conv_src(X.buf, C, ops.TAPS_1X1, scale=sc, shift=sh)], H, W, qkv, bind_qkv,
                    out_mode=ops.OUT_NHWC, bias=bqkv)
+        if T == 256 and C == 256 and not getattr(self, 'unfused_attention', False):
+            # fused core (ddg_attention_fwd): QK^T -> softmax -> PV -> NIN_3 + residual in one kernel per (sample, 128 queries);
+            # logits / weights / attention output never leave the SM and there are no per-image operand packs
+            w3 = ops.ConvWeights(C, [(C, 1)], self.dev, precision=self.prec, nt=256)
+            self.binders.append(lambda: w3.pack_nin_weight(0, Pm[Pn + 'NIN_3.W']))
+            out = Act(self, C, H, W)
+            d = ops.attention_desc(qkv, w3, Pm[Pn + 'NIN_3.b'], X.buf, out.buf, out.stats, N, H, W, C,
+                                   RSQRT2 if self.cfg.skip_rescale else 1.0, precision=self.prec)
+            self._step(lambda d=d: ops.attention_launch(d), name=f'attn_fused {H}x{W} C={C}')
+            self.conv_flops += 2 * N * T * T * C * 2 + 2 * N * T * C * C
+            self._keep.append((w3, d, qkv, wqkv, bqkv))
+            return out
         # per-image K operand: B[co = key t][ci = channel]
         wk = ops.ConvWeights(T, [(C, 1)], self.dev, precision=self.prec, batch=N, m_rows=N * T)
         self._step(lambda: wk.pack_segment(0, qkv, C, 3 * C, 1, 0, w_batch_stride=T * 3 * C, elem_offset=C))

@@ -394,6 +394,28 @@ def spatial_sum(x, act=ACT_NONE, out=None):
     return out
 
 
+def attention_desc(qkv, w3: 'ConvWeights', bias, res, out, stats, n, h, w, c, out_scale, precision=3):
+    d = _lib.AttnDesc()
+    d.qkv = ptr(qkv); d.w3pack = ptr(w3.buf); d.bias = _addr(bias); d.res = _addr(res); d.out = _addr(out); d.stats = _addr(stats)
+    d.N, d.H, d.W, d.C = n, h, w, c
+    d.out_scale = out_scale
+    d.precision = precision
+    assert w3.nt == 256 and w3.cout == c and tuple(w3.segs) == ((c, 1),)
+    return d
+
+
+def attention_launch(desc):
+    """Fused attention core (ddg_attention_fwd): 256 tokens x 256 channels."""
+    if PROFILE['on']:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        check(lib().ddg_attention_fwd(C.byref(desc), stream()), 'attention_fwd')
+        b.record()
+        PROFILE['records'].append(('attn_tc', 2.0 * desc.N * 256 * 256 * 256 * 3, a, b))
+        return
+    check(lib().ddg_attention_fwd(C.byref(desc), stream()), 'attention_fwd')
+
+
 def softmax_rows(s, p, rows, T, lds, ldp):
     check(lib().ddg_softmax_rows(ptr(s), ptr(p), rows, T, lds, ldp, stream()), 'softmax_rows')
     return p
@@ -463,10 +485,10 @@ class ConvWeights:
 
     segs: list of (C_padded, ntaps).  Call pack_segment() for each segment whenever the fp32 weights change."""
 
-    def __init__(self, cout: int, segs, device, precision: int = 3, batch: int = 1, m_rows: int = 0):
-        """m_rows: GEMM rows of the conv that will consume these weights (picks the output-channel tile width)."""
+    def __init__(self, cout: int, segs, device, precision: int = 3, batch: int = 1, m_rows: int = 0, nt: int = 0):
+        """m_rows: GEMM rows of the conv that will consume these weights (picks the output-channel tile width); nt forces it."""
         self.cout = cout
-        self.nt = lib().ddg_conv_tile_n(cout, m_rows)
+        self.nt = nt if nt else lib().ddg_conv_tile_n(cout, m_rows)
         self.segs = list(segs)
         self.precision = precision
         self.batch = batch

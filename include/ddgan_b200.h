@@ -186,6 +186,24 @@ int ddg_conv2d_fwd(const ddg_conv_desc* desc, cudaStream_t stream);
 /* diagnostics: which kernel variant the last ddg_conv2d_fwd call on this host thread launched (tests assert on it) */
 int ddg_conv_last_launch_info(int* msub, int* nt, int* persistent, int* grid_ctas);
 
+/* Fused attention core of AttnBlockpp (layerspp.py:108-124) for 256 tokens x 256 channels (the 16x16 attention level):
+ *   out = (res + NIN_3(softmax(q k^T / sqrt(C)) v) + bias) * out_scale, written PNHWC, + GroupNorm statistics of the result.
+ * qkv: fp32 [N][T][3C] = q | k | v per token (the NHWC output of the fused q/k/v 1x1 conv); w3pack: NIN_3 weights packed by
+ * ddg_conv_pack_weights with nt = 256 (one segment of C channels, 1 tap).  One CTA per (sample, 128 queries): logits, softmax
+ * weights and the attention output stay in TMEM / shared memory. */
+typedef struct {
+  const float* qkv;
+  const void* w3pack;
+  const float* bias;   /* [C] or NULL */
+  const float* res;    /* PNHWC [N][H+2][W+2][C] or NULL */
+  float* out;          /* PNHWC */
+  double* stats;       /* [N][C][2] or NULL */
+  int N, H, W, C;
+  float out_scale;
+  int precision;       /* 3 = BF16x3, 1 = BF16 */
+} ddg_attn_desc;
+int ddg_attention_fwd(const ddg_attn_desc* desc, cudaStream_t stream);
+
 /* Weight gradient of the same convolution (cuDNN wgrad in the reference's backward, ddgan.py:459-506):
  *   dw[co*s_co + ci*s_ci + tap*s_tap] += sum_q dy[q][co] * x[q + tap_dr*Wp + tap_ds][ci]   over the padded space [N][Hp][Wp]
  * x: PNHWC source as seen by the conv (pitch xpitch, Cin_pad channels used, Cin_real scattered);

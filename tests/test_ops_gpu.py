@@ -339,3 +339,36 @@ def test_batched_gemm_attention_core(ops):
     o = torch.zeros(n, T, c, device=DEV)
     ops.conv2d_fused(wv, [ops.conv_src(p, Tp, ops.TAPS_1X1, padded=False)], n, 1, T, o, out_mode=ops.OUT_NHWC, batch_rows=T)
     assert O.rel_l2(o.cpu(), ref_o) < 3e-5
+
+
+@pytest.mark.parametrize('n,prec,tol', [(2, 3, 2e-5), (5, 3, 2e-5), (3, 1, 1e-2)])
+def test_fused_attention_core(n, prec, tol):
+    """ddg_attention_fwd (QK^T -> softmax -> PV -> NIN_3 + residual, one kernel) against the einsum formulation of
+    layerspp.py:115-124 in fp32 on the CPU; 16x16 tokens, 256 channels."""
+    from ddgan_b200 import ops
+    import math
+    H = W = 16; C = 256; T = H * W
+    g = torch.Generator().manual_seed(77 + n)
+    qkv = torch.randn(n, T, 3 * C, generator=g) * 1.3
+    W3 = torch.randn(C, C, generator=g) / math.sqrt(C)
+    b3 = torch.randn(C, generator=g) * 0.1
+    x = torch.randn(n, C, H, W, generator=g)
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    w = torch.softmax(torch.einsum('btc,bsc->bts', q, k) * (C ** -0.5), dim=-1)
+    h = torch.einsum('bts,bsc->btc', w, v)
+    ref = (x + (h @ W3 + b3).transpose(1, 2).reshape(n, C, H, W)) / math.sqrt(2.0)
+    xp = ops.to_pnhwc(x.to(DEV), cpad=C)
+    out = ops.alloc_pnhwc(n, H, W, C, DEV)
+    st = torch.zeros(n, C, 2, dtype=torch.float64, device=DEV)
+    w3 = ops.ConvWeights(C, [(C, 1)], DEV, precision=prec, nt=256)
+    w3.pack_nin_weight(0, W3.to(DEV))
+    d = ops.attention_desc(qkv.to(DEV), w3, b3.to(DEV), xp, out, st, n, H, W, C, 1.0 / math.sqrt(2.0), precision=prec)
+    ops.attention_launch(d)
+    y = ops.from_pnhwc(out, C).cpu()
+    err = float((y - ref).norm() / ref.norm())
+    assert err < tol, err
+    if prec == 3:
+        assert torch.allclose(st[..., 0].cpu(), ref.double().sum(dim=(2, 3)), rtol=1e-4, atol=1e-3)
+        assert torch.allclose(st[..., 1].cpu(), (ref.double() ** 2).sum(dim=(2, 3)), rtol=1e-4, atol=1e-3)
+    # border of the PNHWC output stays zero
+    assert float(out[:, 0].abs().max()) == 0.0 and float(out[:, :, 0].abs().max()) == 0.0
