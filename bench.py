@@ -318,7 +318,7 @@ def conv_roofline(eng, pk, pk_kind, reps=3):
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
         for i, st in enumerate(eng.steps):
-            if eng.step_names[i].startswith('conv'):
+            if eng.step_names[i].startswith(('conv', 'attn_fused')):
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(); st(); b.record()
                 pairs.append((a, b))
@@ -331,11 +331,11 @@ def conv_roofline(eng, pk, pk_kind, reps=3):
             total_ms_eager += s0.elapsed_time(s1)
     conv_ms /= (reps - 1)
     total_ms_eager /= (reps - 1)
-    n_conv = len([n for n in eng.step_names if n.startswith('conv')])
+    n_conv = len([n for n in eng.step_names if n.startswith(('conv', 'attn_fused'))])
     achieved = eng.conv_flops / (conv_ms * 1e-3) / 1e12
     peak = pk.get('bf16_tflops_sustained', pk['bf16_tflops'])
     prec3 = eng.prec == 3
-    roof = {'bound': 'tensor', 'kernel': 'conv_tc_kernel (all instantiations, %d launches per generator forward)' % n_conv,
+    roof = {'bound': 'tensor', 'kernel': 'conv_tc_kernel (all instantiations) + attn_kernel, %d tensor-core launches per generator forward' % n_conv,
             'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
             'peak_source': f'{pk_kind} bf16_tflops_sustained (kernel timed inside a long step)',
             'flops_per_forward': eng.conv_flops, 'conv_ms_per_forward': conv_ms, 'eager_forward_ms': total_ms_eager,
