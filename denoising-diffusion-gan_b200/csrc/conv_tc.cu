@@ -27,6 +27,7 @@
 //     sets in TMEM and four dedicated epilogue warps overlap the epilogue of tile i with the mainloop of tile i + 1,
 //     setmaxnreg moves registers from the single-thread roles to the producer warpgroups.
 #include <cstdlib>
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 #include "common.cuh"
 #include "ddgan_b200.h"
 
@@ -64,6 +65,14 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+
+// 5-D tiled TMA load (tensor map in kernel-parameter space): box -> shared memory, completion on an mbarrier
+__device__ __forceinline__ void tma_tensor_5d_g2s(uint32_t dst, const void* tmap, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
+      : "memory");
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -168,6 +177,8 @@ struct SrcDev {
   int ntaps;
   int padded;     // gather mode only: source is padded NHWC
   int tapoff[9];  // window mode: row offset of each tap relative to the window start
+  int tma;        // 1: this K segment's A operand comes from pre-split bf16 planes through the TMA engine (2-D tiling only)
+  int chunk0;     // first 8-channel chunk of the segment inside the planes tensor
 };
 
 struct ConvDev {
@@ -202,6 +213,10 @@ struct ConvDev {
   int tiles_m, n_tiles;        // persistent variant: tile = n_tile * tiles_m + m_tile, CTA b runs tiles b, b + grid, ...
   long w_batch_stride;         // bytes between the packed B operands of consecutive batches
   int nsa;                     // A-operand ring depth (2..4 stages, whatever the shared-memory budget allows)
+  int tma_pitch;               // chunk pitch of a TMA-written A plane: window rows * 16 bytes, dense (producer planes are padded)
+  void* out_planes;            // optional pre-split copy of the PNHWC output (see ddg_conv_desc.out_planes)
+  long out_plane_bytes;
+  alignas(64) CUtensorMap tmap[DDG_CONV_MAX_SRC][2];   // hi / lo plane of every TMA-fed source
 };
 
 constexpr int kProdWarps = 8;
@@ -301,7 +316,7 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
   };
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 4; ++s) { mbar_init(fullA(s), kProdWarps); mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(fullA(s), kProdWarps + 1); mbar_init(emptyA(s), 1); }   // 8 producer warps + the loader
     for (int s = 0; s < NSB; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(accFull(b), 1); mbar_init(accEmpty(b), PERSIST ? 4 : kProdWarps); }
     fence_barrier_init();
@@ -408,6 +423,22 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
               float4* o4 = reinterpret_cast<float4*>(p.out + obase + col0);
 #pragma unroll
               for (int j = 0; j < CW / 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (p.out_planes != nullptr && full && p.out_mode == 0) {
+                // the same values once more as bf16 hi / lo planes [n][chunk][h+1][w+1][8]: consumers that take this tensor without a
+                // prologue (1x1 skip convs) fetch them with the TMA engine instead of converting fp32 in their producer warps
+                const size_t img = (size_t)(p.Hout + 2) * (p.Wout + 2);
+                const size_t pix = (size_t)(h + 1) * (p.Wout + 2) + (w + 1);
+                uint8_t* pb = reinterpret_cast<uint8_t*>(p.out_planes);
+#pragma unroll
+                for (int q = 0; q < CW / 8; ++q) {
+                  uint4 hi, lo;
+                  split_bf16x2(v[8 * q], v[8 * q + 1], hi.x, lo.x); split_bf16x2(v[8 * q + 2], v[8 * q + 3], hi.y, lo.y);
+                  split_bf16x2(v[8 * q + 4], v[8 * q + 5], hi.z, lo.z); split_bf16x2(v[8 * q + 6], v[8 * q + 7], hi.w, lo.w);
+                  const size_t off = (((size_t)n * (p.out_C / 8) + (col0 / 8 + q)) * img + pix) * 16;
+                  *reinterpret_cast<uint4*>(pb + off) = hi;
+                  if (NPL == 2) *reinterpret_cast<uint4*>(pb + p.out_plane_bytes + off) = lo;
+                }
+              }
             } else {
 #pragma unroll
               for (int j = 0; j < CW; ++j) {
@@ -584,7 +615,7 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
     float cur[IMAX][8], nxt[IMAX][8];
     int off_c[IMAX], nn_c[IMAX], off_n[IMAX], nn_n[IMAX];
     int s_cur = 0, kb_cur = 0;
-    {
+    if (!p.src[0].tma) {
       int lo_, hi_;
       src_rows(p.src[0], lo_, hi_);
 #pragma unroll
@@ -622,7 +653,7 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
       int s_nxt = s_cur, kb_nxt = kb_cur + 1;
       if (kb_nxt >= S.C / KB) { s_nxt = s_cur + 1; kb_nxt = 0; }
       const bool has_next = kb_idx + 1 < nkb_total;
-      if (has_next) {
+      if (has_next && !p.src[s_nxt].tma) {
         const SrcDev& Sn = p.src[s_nxt];
         if (s_nxt != s_cur) {
           int lo_, hi_;
@@ -654,9 +685,10 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
       uint8_t* dst_lo = dst_hi + a_plane;
       int row_lo, row_hi;
       src_rows(S, row_lo, row_hi);
+      if (S.tma) row_hi = row_lo;       // TMA-fed K segment: the loader thread fills this stage; the producers only keep the barrier count
 #pragma unroll
       for (int k = 0; k < IMAX; ++k) {
-        if (off_c[k] != -2) transform_store(S, cur[k], off_c[k] >= 0, nn_c[k], ch0, cur_n, sc, sh, dst_hi, dst_lo, row_lo + e0 + k * ESTEP);
+        if (!S.tma && off_c[k] != -2) transform_store(S, cur[k], off_c[k] >= 0, nn_c[k], ch0, cur_n, sc, sh, dst_hi, dst_lo, row_lo + e0 + k * ESTEP);
       }
       // rows beyond the register pipeline (very wide windows only)
       for (int e = row_lo + e0 + IMAX * ESTEP; e < row_hi; e += ESTEP) {
@@ -722,16 +754,35 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
       long long w_emptyB = 0;
       const long long t_l0 = DDG_CLK();
       uint32_t gb = 0;                                 // B stages issued so far (ring position / parity across tiles)
+      int stA_l = 0; uint32_t phA_l = 0;               // A ring position / parity: one arrival per K block (with the TMA bytes when TMA-fed)
+      const uint32_t tma_plane = (uint32_t)(KCH * p.tma_pitch);
       for (int tile = tile_first; tile < tile_end; tile += tile_stride) {
         set_tile(tile);
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)ntile * p.total_stages * Cfg::B_STAGE +
                               (p.batch_rows > 0 ? (size_t)blockIdx.z * p.w_batch_stride : 0);
-        for (int i = 0; i < p.total_stages; ++i, ++gb) {
-          const int st = gb % NSB;
-          const uint32_t ph = (gb / NSB) & 1;
-          { const long long tw = DDG_CLK(); mbar_wait(emptyB(st), ph ^ 1); w_emptyB += DDG_CLK() - tw; }
-          mbar_arrive_expect_tx(fullB(st), Cfg::B_STAGE);
-          tma_bulk_g2s(smem_u32(sB + st * Cfg::B_STAGE), wsrc + (size_t)i * Cfg::B_STAGE, Cfg::B_STAGE, fullB(st));
+        int i = 0;
+        for (int s = 0; s < p.nsrc; ++s) {
+          const SrcDev& S = p.src[s];
+          for (int kb = 0; kb < S.C / KB; ++kb) {
+            mbar_wait(emptyA(stA_l), phA_l ^ 1);
+            if (S.tma) {
+              // halo window (16*MSUB+2 rows x 10 columns) x 4 chunks of 8 channels, from the padded planes [n][chunk][y][x][8]
+              const uint32_t dst = smem_u32(sA + stA_l * a_stage);
+              mbar_arrive_expect_tx(fullA(stA_l), NPL * tma_plane);
+              tma_tensor_5d_g2s(dst, &p.tmap[s][0], 0, t2_x0, t2_y0, S.chunk0 + kb * KCH, t2_n, fullA(stA_l));
+              if (NPL == 2) tma_tensor_5d_g2s(dst + (uint32_t)a_plane, &p.tmap[s][1], 0, t2_x0, t2_y0, S.chunk0 + kb * KCH, t2_n, fullA(stA_l));
+            } else {
+              mbar_arrive(fullA(stA_l));
+            }
+            if (++stA_l == NSA) { stA_l = 0; phA_l ^= 1u; }
+            for (int t = 0; t < S.ntaps; ++t, ++i, ++gb) {
+              const int st = gb % NSB;
+              const uint32_t ph = (gb / NSB) & 1;
+              { const long long tw = DDG_CLK(); mbar_wait(emptyB(st), ph ^ 1); w_emptyB += DDG_CLK() - tw; }
+              mbar_arrive_expect_tx(fullB(st), Cfg::B_STAGE);
+              tma_bulk_g2s(smem_u32(sB + st * Cfg::B_STAGE), wsrc + (size_t)i * Cfg::B_STAGE, Cfg::B_STAGE, fullB(st));
+            }
+          }
         }
       }
       if (PROF && p.prof != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0) {
@@ -752,9 +803,7 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
       // SBO = byte distance between 8-row groups (128 B linear tiles, 160 B for 2-D tiles).  Verified on B200.
       const uint32_t a_hi32 = ((uint32_t)p.a_sbo >> 4) | (1u << 14);                 // descriptor bits 32..63
       const uint32_t b_hi32 = (128u >> 4) | (1u << 14);
-      const uint32_t a_lbo_f = (((uint32_t)p.win_pitch >> 4) & 0x3FFF) << 16;         // LBO field of the low word
       const uint32_t b_lbo_f = (((uint32_t)(NT * 16) >> 4) & 0x3FFF) << 16;
-      const uint32_t a_kk16 = (2u * (uint32_t)p.win_pitch) >> 4;                      // +16 channels, in 16-byte units
       constexpr uint32_t b_kk16 = (2u * NT * 16u) >> 4;
       const uint32_t a_sub16 = (uint32_t)p.sub_stride >> 4;
       uint32_t bi = 0;                                 // B stages consumed so far (ring position across tiles)
@@ -775,8 +824,12 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
         const int stA = stA_m;
         { const long long tw = DDG_CLK(); mbar_wait(fullA(stA), phA_m); w_fullA += DDG_CLK() - tw; }
         if (++stA_m == NSA) { stA_m = 0; phA_m ^= 1u; }
-        const uint32_t a_hi_lo = a_lbo_f | ((smem_u32(sA + stA * a_stage) >> 4) & 0x3FFFu);
-        const uint32_t a_lo_lo = a_lbo_f | ((smem_u32(sA + stA * a_stage + a_plane) >> 4) & 0x3FFFu);
+        // TMA-written stages are dense ([chunk][window row][16 B], pitch = rows * 16); producer-written ones carry the bank padding
+        const uint32_t pitch_s = S.tma ? (uint32_t)p.tma_pitch : (uint32_t)p.win_pitch;
+        const uint32_t a_lbo_s = ((pitch_s >> 4) & 0x3FFF) << 16;
+        const uint32_t a_kk16_s = (2u * pitch_s) >> 4;
+        const uint32_t a_hi_lo = a_lbo_s | ((smem_u32(sA + stA * a_stage) >> 4) & 0x3FFFu);
+        const uint32_t a_lo_lo = a_lbo_s | ((smem_u32(sA + stA * a_stage + a_plane) >> 4) & 0x3FFFu);
         for (int t = 0; t < S.ntaps; ++t, ++bi) {
           const int stB = bi % NSB;
           { const long long tw = DDG_CLK(); mbar_wait(fullB(stB), (bi / NSB) & 1); w_fullB += DDG_CLK() - tw; }
@@ -791,7 +844,7 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
               uint32_t acc_s = acc;
 #pragma unroll
               for (int kk = 0; kk < KB / 16; ++kk) {
-                const uint32_t ao = toff16 + (uint32_t)sub * a_sub16 + (uint32_t)kk * a_kk16;
+                const uint32_t ao = toff16 + (uint32_t)sub * a_sub16 + (uint32_t)kk * a_kk16_s;
                 const uint32_t bo = (uint32_t)kk * b_kk16;
                 if (PREC == 3) {
                   umma_bf16_lohi(d, a_lo_lo + ao, a_hi32, b_hi_lo + bo, b_hi32, idesc, acc_s);
@@ -907,7 +960,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
 struct Variant { int msub, nt, kb; };
 
 static int g_small_nt64 = 1;
-static thread_local int g_last_info[4] = {0, 0, 0, 0};   // msub, nt, persistent, CTAs of the last launch
+static thread_local int g_last_info[5] = {0, 0, 0, 0, 0};   // msub, nt, persistent, CTAs, TMA-fed K segments of the last launch
 static int g_persist = getenv("DDG_CONV_NO_PERSIST") ? 0 : 1;   // persistent variant (epilogue overlapped with the next tile's mainloop) when tiles > SMs
 static int num_sms() {
   static int n = 0;
@@ -969,11 +1022,76 @@ static int launch_conv(ConvDev& d, int n_tiles, cudaStream_t stream) {
   return DDG_OK;
 }
 
+// fp32 PNHWC -> pre-split bf16 planes [plane][N][C/8][H+2][W+2][8] (interior only).  One thread per (pixel, 8-channel chunk), pixels
+// fastest: 32-byte reads (one sector each), 16-byte writes contiguous across the warp.
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, uint8_t* __restrict__ planes, int N, int H, int W, int C,
+                                                          int nplanes, long plane_bytes) {
+  const int C8 = C / 8;
+  const long total = (long)N * C8 * H * W;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H); r /= H;
+    const int ch = (int)(r % C8);
+    const int n = (int)(r / C8);
+    const size_t pix = (size_t)(n * (H + 2) + h + 1) * (W + 2) + (w + 1);
+    const float4* src = reinterpret_cast<const float4*>(x + pix * C + ch * 8);
+    const float4 a = __ldg(src), b = __ldg(src + 1);
+    uint4 hi, lo;
+    split_bf16x2(a.x, a.y, hi.x, lo.x); split_bf16x2(a.z, a.w, hi.y, lo.y);
+    split_bf16x2(b.x, b.y, hi.z, lo.z); split_bf16x2(b.z, b.w, hi.w, lo.w);
+    const size_t off = (((size_t)n * C8 + ch) * (size_t)(H + 2) * (W + 2) + (size_t)(h + 1) * (W + 2) + (w + 1)) * 16;
+    *reinterpret_cast<uint4*>(planes + off) = hi;
+    if (nplanes == 2) *reinterpret_cast<uint4*>(planes + plane_bytes + off) = lo;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  return fn;
+}
+static int g_use_tma = getenv("DDG_CONV_NO_TMA") ? 0 : 1;
+
+// planes [N][Ct/8][Hp][Wp][8] bf16 as a 5-D tensor (innermost first: 8, Wp, Hp, Ct/8, N); box = 8 x 10 x rows x 4 chunks x 1
+static bool encode_plane_map(CUtensorMap* m, const void* base, int N, int Hp, int Wp, int Ct, int box_rows) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t dims[5] = {8, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)(Ct / 8), (cuuint64_t)N};
+  const cuuint64_t strides[4] = {16, (cuuint64_t)Wp * 16, (cuuint64_t)Hp * Wp * 16, (cuuint64_t)(Ct / 8) * Hp * Wp * 16};
+  const cuuint32_t box[5] = {8, 10, (cuuint32_t)box_rows, 4, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace ddg
 
 using namespace ddg;
 
+extern "C" long ddg_planes_bytes(int N, int H, int W, int C) { return (long)N * (C / 8) * (H + 2) * (W + 2) * 16; }
+
+extern "C" int ddg_split_planes(const float* x, void* planes, int N, int H, int W, int C, int nplanes, cudaStream_t stream) {
+  if (!x || !planes || C % 8 != 0 || nplanes < 1 || nplanes > 2) { ddg_set_last_error("split_planes: bad args"); return DDG_ERR_ARG; }
+  const long total = (long)N * (C / 8) * H * W;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148L * 32) blocks = 148L * 32;
+  split_planes_kernel<<<(int)blocks, 256, 0, stream>>>(x, (uint8_t*)planes, N, H, W, C, nplanes, ddg_planes_bytes(N, H, W, C));
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}
+
 extern "C" int ddg_conv_tile_n(int cout, long m_rows) { return pick_nt(cout, m_rows); }
+extern "C" int ddg_conv_last_launch_tma(void) { return g_last_info[4]; }
 extern "C" int ddg_conv_last_launch_info(int* msub, int* nt, int* persistent, int* grid_ctas) {
   if (msub) *msub = g_last_info[0];
   if (nt) *nt = g_last_info[1];
@@ -1123,6 +1241,22 @@ extern "C" int ddg_conv2d_fwd(const ddg_conv_desc* c, cudaStream_t stream) {
   rows += (10 - (rows & 7)) & 7;                    // pitch = 32 (mod 128) bytes: the 4 chunks x 2 rows of a 16-byte store phase hit 8 distinct bank groups
   d.win_pitch = rows * 16;
   const int prec = c->precision == 1 ? 1 : 3;
+  // TMA-fed K segments: prologue-free sources that come with pre-split planes, 2-D tiling only (the halo window is a 5-D box)
+  d.tma_pitch = d.win_rows * 16;
+  for (int s = 0; s < c->nsrc; ++s) {
+    const ddg_conv_src& S = c->src[s];
+    d.src[s].tma = 0;
+    d.src[s].chunk0 = 0;
+    if (!g_use_tma || !tile2d || !S.planes || S.scale || S.act != 0 || S.planes_C % 8 != 0 || S.planes_c0 % 8 != 0) continue;
+    const long pb = ddg_planes_bytes(d.N, d.Hout, d.Wout, S.planes_C);
+    bool ok = encode_plane_map(&d.tmap[s][0], S.planes, d.N, d.Hout + 2, d.Wout + 2, S.planes_C, 16 * msub + 2);
+    if (ok && prec == 3) ok = encode_plane_map(&d.tmap[s][1], (const uint8_t*)S.planes + pb, d.N, d.Hout + 2, d.Wout + 2, S.planes_C, 16 * msub + 2);
+    if (ok) { d.src[s].tma = 1; d.src[s].chunk0 = S.planes_c0 / 8; }
+  }
+  g_last_info[4] = 0;
+  for (int s = 0; s < c->nsrc; ++s) g_last_info[4] += d.src[s].tma;
+  d.out_planes = (c->out_mode == 0) ? c->out_planes : nullptr;
+  d.out_plane_bytes = ddg_planes_bytes(d.N, d.Hout, d.Wout, d.out_C);
 
   // tuning builds with cycle counters (tools/conv_prof.py): the three shapes that dominate a generator forward
   if (d.prof != nullptr && prec == 3) {

@@ -18,7 +18,8 @@ MAX_SRC = 3
 
 class ConvSrc(C.Structure):
     _fields_ = [('x', C.c_void_p), ('scale', C.c_void_p), ('shift', C.c_void_p), ('C', C.c_int), ('pitch', C.c_int), ('ss_stride', C.c_int), ('act', C.c_int),
-                ('ntaps', C.c_int), ('padded', C.c_int), ('tap_dr', C.c_int8 * 9), ('tap_ds', C.c_int8 * 9)]
+                ('ntaps', C.c_int), ('padded', C.c_int), ('tap_dr', C.c_int8 * 9), ('tap_ds', C.c_int8 * 9),
+                ('planes', C.c_void_p), ('planes_C', C.c_int), ('planes_c0', C.c_int)]
 
 
 class ConvDesc(C.Structure):
@@ -27,7 +28,7 @@ class ConvDesc(C.Structure):
                 ('bias', C.c_void_p), ('addvec', C.c_void_p), ('addvec_stride', C.c_int), ('res', C.c_void_p),
                 ('out_scale', C.c_float), ('out_act', C.c_int), ('out', C.c_void_p), ('out_mode', C.c_int),
                 ('out_C', C.c_int), ('stats', C.c_void_p), ('precision', C.c_int), ('msub', C.c_int),
-                ('force_linear', C.c_int), ('debug_prof', C.c_void_p), ('batch_rows', C.c_int)]
+                ('force_linear', C.c_int), ('debug_prof', C.c_void_p), ('batch_rows', C.c_int), ('out_planes', C.c_void_p)]
 
 
 class WgradDesc(C.Structure):
@@ -81,6 +82,7 @@ _SIGNATURES = {
     'ddg_minibatch_stddev': ([_P, _P] + [_I] * 6 + [_P], _I),
     'ddg_spatial_sum': ([_P, _P] + [_I] * 5 + [_P], _I),
     'ddg_conv_last_launch_info': ([_P, _P, _P, _P], _I),
+    'ddg_conv_last_launch_tma': ([], _I),
     'ddg_zero_border': ([_P] + [_I] * 4 + [_P], _I),
     'ddg_softmax_rows': ([_P, _P, _L, _I, _I, _I, _P], _I),
     'ddg_conv_tile_n': ([_I, _L], _I),
@@ -94,6 +96,8 @@ _SIGNATURES = {
     'ddg_s2d_weights': ([_P, _P, _I, _I, _I, _I, _P], _I),
     'ddg_images_to_u8': ([_P, _P, _I, _I, _I, _I, _F, _F, _P], _I),
     'ddg_conv2d_fwd': ([C.POINTER(ConvDesc), _P], _I),
+    'ddg_split_planes': ([_P, _P, _I, _I, _I, _I, _I, _P], _I),
+    'ddg_planes_bytes': ([_I, _I, _I, _I], _L),
     'ddg_conv2d_wgrad': ([C.POINTER(WgradDesc), _P], _I),
     'ddg_attention_fwd': ([C.POINTER(AttnDesc), _P], _I),
     'ddg_affine_act_fwd': ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),

@@ -35,6 +35,8 @@ class Act:
         self.C, self.H, self.W = c, h, w
         self.buf = ops.alloc_pnhwc(eng.N, h, w, c, eng.dev)
         self.stats = eng._alloc_stats(c) if stats else None
+        self.planes = None      # pre-split bf16 copy (ops.alloc_planes), created on demand by _EngineBase._planes_of
+        self.producer = None    # conv descriptor that writes this activation (PNHWC), if any: it can write the planes too
 
 
 def _groups(c):
@@ -94,6 +96,7 @@ class _EngineBase:
         m_rows = n * kw.get('hp', hout + 2) * kw.get('wp', wout + 2) if window else n * hout * wout
         cw = ops.ConvWeights(cout, [(s['C'], len(s['taps'])) for s in srcs], self.dev, precision=self.prec, m_rows=m_rows)
         desc = ops.build_conv_desc(cw, srcs, n, hout, wout, out, **kw)
+        self._last_desc = desc
         self._keep.append((cw, desc, srcs, kw, out))
         if binder is not None:
             self.binders.append(lambda cw=cw: binder(cw))
@@ -103,6 +106,26 @@ class _EngineBase:
         self.conv_flops += 2 * n * hout * wout * cout * sum(s['C'] * len(s['taps']) for s in srcs)
         self.conv_bytes += 4 * n * hout * wout * (sum(s['C'] for s in srcs) + cout * (2 if kw.get('res') is not None else 1)) + cw.bytes_per_batch
         return cw
+
+    def _planes_of(self, act):
+        """Pre-split bf16 planes of an activation for consumers that read it raw (1x1 skip convs): written by the producing conv's
+        epilogue when there is one (no extra pass), else by a split kernel placed here in the plan.  None when the geometry is
+        not the 2-D tiling the TMA path covers (H % 16, W % 8)."""
+        # Measured on B200 (CIFAR NCSN++, batch 64, whole sampling step): BF16 mode 4529 -> 4612 images/s with the planes (the TMA
+        # moves half the bytes of the fp32 path and no conversion is left); BF16x3 mode 3831 -> 3760 (hi + lo planes are as many
+        # bytes as the fp32 rows, so only the conversion is saved, and the extra epilogue stores / split passes cost more than
+        # that).  Hence: on by default in BF16 mode only; DDG_ENGINE_PLANES=0/1 overrides.
+        want = os.environ.get('DDG_ENGINE_PLANES')
+        on = (self.prec == 1) if want is None else (want == '1')
+        if not on or act.H % 16 != 0 or act.W % 8 != 0:
+            return None
+        if act.planes is None:
+            act.planes = ops.alloc_planes(self.N, act.H, act.W, act.C, self.prec, self.dev)
+            if act.producer is not None:
+                act.producer.out_planes = act.planes.data_ptr()
+            else:
+                self._step(lambda a=act: ops.split_planes(a.buf, a.planes, self.prec), name='split_planes')
+        return act.planes
 
     def _linear_rows(self, x, k, w, b, out, act_in=ops.ACT_NONE):
         """out[N][J] = act_in(x[N][k]) @ w[J][k]^T + b as one tensor-core GEMM (rows = batch samples); w is re-packed by a binder
@@ -250,6 +273,7 @@ class GeneratorEngine(_EngineBase):
         self._conv(nf, [ops.conv_src(xin.buf, cp_in, ops.TAPS_3X3)], S, S, h0.buf,
                    lambda cw, nme=nme: cw.pack_segment(0, P[nme + '.weight'], cfg.num_channels, cfg.num_channels * 9, 9, 1),
                    bias=P[nme + '.bias'], stats=h0.stats)
+        h0.producer = self._last_desc
         hs = [h0]
         pyramid = xin
         h = h0
@@ -354,7 +378,7 @@ class GeneratorEngine(_EngineBase):
             # K segments: the 3x3 over the normalised h1, then the 1x1 skip conv over the raw block input(s).  (Measured: putting the
             # 1-tap segments first, so that they would be produced under the previous tile's 3x3 MMAs, is 2 % slower end to end.)
             skip_first = os.environ.get('DDG_SKIP_SEG_FIRST') is not None
-            skip_srcs = [ops.conv_src(xs.buf, xs.C, ops.TAPS_1X1) for xs in skip]
+            skip_srcs = [ops.conv_src(xs.buf, xs.C, ops.TAPS_1X1, planes=self._planes_of(xs)) for xs in skip]
             src1 = skip_srcs + src1 if skip_first else src1 + skip_srcs
             i3 = len(skip_srcs) if skip_first else 0
             i1 = 0 if skip_first else 1
@@ -372,6 +396,7 @@ class GeneratorEngine(_EngineBase):
             assert len(X) == 1
             self._conv(out_ch, src1, H, W, out.buf, lambda cw: cw.pack_conv_weight(0, Pm[Pn + 'Conv_1.weight']),
                        bias=Pm[Pn + 'Conv_1.bias'], res=X[0].buf, out_scale=scale, stats=out.stats)
+        out.producer = self._last_desc
         return out
 
     def _attn(self, m, X):
@@ -428,6 +453,7 @@ class GeneratorEngine(_EngineBase):
         self._conv(C, [ops.conv_src(o, C, ops.TAPS_1X1, padded=False)], H, W, out.buf,
                    lambda cw: cw.pack_nin_weight(0, Pm[Pn + 'NIN_3.W']), bias=Pm[Pn + 'NIN_3.b'], res=X.buf,
                    out_scale=RSQRT2 if self.cfg.skip_rescale else 1.0, stats=out.stats)
+        out.producer = self._last_desc
         return out
 
     def _pyramid_down(self, m, pyr, h):
@@ -453,6 +479,7 @@ class GeneratorEngine(_EngineBase):
         scale = RSQRT2 if self.cfg.skip_rescale else 1.0
         self._conv(cout, [ops.conv_src(s2d, 4 * cp, ops.TAPS_2X2)], Ho, Wo, out.buf, bind, hp=Ho + 3, wp=Wo + 3,
                    bias=Pm[Pn + '.bias'], res=h.buf, out_scale=scale, stats=out.stats)
+        out.producer = self._last_desc
         self._keep.append((s2d, w2))
         return out
 

@@ -528,9 +528,23 @@ class ConvWeights:
         self.pack_segment(i, W, W.shape[0], 1, W.shape[1], 0)
 
 
-def conv_src(x, c, taps, scale=None, shift=None, act=ACT_NONE, padded=True, pitch=0, ss_stride=0):
-    """x / scale / shift may be tensors or raw device addresses (ints) for channel-sliced views."""
-    return dict(x=x, C=c, taps=taps, scale=scale, shift=shift, act=act, padded=padded, pitch=pitch, ss_stride=ss_stride)
+def conv_src(x, c, taps, scale=None, shift=None, act=ACT_NONE, padded=True, pitch=0, ss_stride=0, planes=None, planes_C=0, planes_c0=0):
+    """x / scale / shift may be tensors or raw device addresses (ints) for channel-sliced views.  planes: optional pre-split bf16
+    copy of the same tensor (alloc_planes layout) -- prologue-free sources only; the kernel then fetches this K segment by TMA."""
+    return dict(x=x, C=c, taps=taps, scale=scale, shift=shift, act=act, padded=padded, pitch=pitch, ss_stride=ss_stride,
+                planes=planes, planes_C=planes_C or c, planes_c0=planes_c0)
+
+
+def alloc_planes(n, h, w, c, precision, device):
+    """Zero-initialised pre-split operand planes of a PNHWC tensor: bf16 [planes][N][C/8][H+2][W+2][8] (planes = 2 for BF16x3)."""
+    npl = 2 if precision == 3 else 1
+    return torch.zeros(npl * lib().ddg_planes_bytes(n, h, w, c), dtype=torch.uint8, device=device)
+
+
+def split_planes(x, planes, precision):
+    n, hp, wp, c = x.shape
+    check(lib().ddg_split_planes(ptr(x), ptr(planes), n, hp - 2, wp - 2, c, 2 if precision == 3 else 1, stream()), 'split_planes')
+    return planes
 
 
 def _addr(v):
@@ -538,7 +552,8 @@ def _addr(v):
 
 
 def build_conv_desc(weights: ConvWeights, srcs, n, hout, wout, out, out_mode=OUT_PNHWC, hp=None, wp=None, bias=None, addvec=None,
-                    addvec_stride=0, res=None, out_scale=1.0, out_act=ACT_NONE, out_c=0, stats=None, msub=0, batch_rows=0, prof=None, force_linear=0) -> ConvDesc:
+                    addvec_stride=0, res=None, out_scale=1.0, out_act=ACT_NONE, out_c=0, stats=None, msub=0, batch_rows=0, prof=None, force_linear=0,
+                    out_planes=None) -> ConvDesc:
     d = ConvDesc()
     d.nsrc = len(srcs)
     for i, s in enumerate(srcs):
@@ -548,6 +563,7 @@ def build_conv_desc(weights: ConvWeights, srcs, n, hout, wout, out, out_mode=OUT
         for t, (dr, ds) in enumerate(s['taps']):
             sd.tap_dr[t] = dr
             sd.tap_ds[t] = ds
+        sd.planes = _addr(s.get('planes')); sd.planes_C = s.get('planes_C', 0) or s['C']; sd.planes_c0 = s.get('planes_c0', 0)
         assert (s['C'], len(s['taps'])) == tuple(weights.segs[i]), 'source / packed-weight segment mismatch'
     d.wpack = ptr(weights.buf)
     d.kb = KB
@@ -565,6 +581,7 @@ def build_conv_desc(weights: ConvWeights, srcs, n, hout, wout, out, out_mode=OUT
     d.batch_rows = batch_rows
     d.debug_prof = _addr(prof)
     d.force_linear = force_linear
+    d.out_planes = _addr(out_planes)
     return d
 
 

@@ -132,6 +132,14 @@ typedef struct {
   int padded;
   int8_t tap_dr[9];    /* row / column offset of every tap relative to the output position */
   int8_t tap_ds[9];
+  /* Optional pre-split operand planes of the SAME tensor (sources without a prologue only): bf16 [planes][N][Ct/8][H+2][W+2][8],
+   * plane 0 = rn_bf16(x), plane 1 (precision 3) = rn_bf16(x - plane 0), zero border, written by a conv epilogue
+   * (ddg_conv_desc.out_planes) or by ddg_split_planes.  When given and the conv runs the 2-D tiling, the A operand of this K
+   * segment is fetched by the TMA engine (cp.async.bulk.tensor 5-D boxes) straight into the UMMA layout -- no conversion work
+   * in the kernel; otherwise the fp32 path is used.  planes_C = Ct (channels of the planes tensor), planes_c0 = first channel of
+   * this segment inside it (multiple of 8). */
+  const void* planes;
+  int planes_C, planes_c0;
 } ddg_conv_src;
 
 typedef struct {
@@ -159,6 +167,8 @@ typedef struct {
   void* debug_prof;    /* optional int64[16] device buffer: per-role cycle counters of one CTA (tuning aid), or NULL */
   int batch_rows;      /* >0: batched GEMM (1x1 only): rows [b*batch_rows, (b+1)*batch_rows) use packed operand b
                           (wpack + b * ddg_conv_packed_bytes(...)); used for the attention GEMMs (layerspp.py:115-119) */
+  void* out_planes;    /* optional (PNHWC output only): also write the result as pre-split bf16 planes [planes][N][out_C/8][H+2][W+2][8]
+                          for consumers that read it without a prologue (see ddg_conv_src.planes) */
 } ddg_conv_desc;
 
 /* output-channel tile width the conv kernel will use for a problem with m_rows GEMM rows (pack and launch must agree) */
@@ -183,8 +193,15 @@ typedef struct {
 long ddg_conv_pack_chunks(int cout, int cin_pad, int ntaps, int kb, int nt);
 int ddg_conv_pack_batch(const ddg_pack_item* items_dev, int n_items, long total_chunks, cudaStream_t stream);
 int ddg_conv2d_fwd(const ddg_conv_desc* desc, cudaStream_t stream);
+/* x: PNHWC fp32 [N][H+2][W+2][C] -> pre-split operand planes (layout above; `planes` = 2 for precision 3, 1 for precision 1);
+ * only the interior is written (the planes buffer is zero-initialised once by its owner). */
+int ddg_split_planes(const float* x, void* planes, int N, int H, int W, int C, int nplanes, cudaStream_t stream);
+/* bytes of one plane of such a buffer */
+long ddg_planes_bytes(int N, int H, int W, int C);
 /* diagnostics: which kernel variant the last ddg_conv2d_fwd call on this host thread launched (tests assert on it) */
 int ddg_conv_last_launch_info(int* msub, int* nt, int* persistent, int* grid_ctas);
+/* ... and how many of its K segments were fetched by the TMA engine from pre-split planes */
+int ddg_conv_last_launch_tma(void);
 
 /* Fused attention core of AttnBlockpp (layerspp.py:108-124) for 256 tokens x 256 channels (the 16x16 attention level):
  *   out = (res + NIN_3(softmax(q k^T / sqrt(C)) v) + bias) * out_scale, written PNHWC, + GroupNorm statistics of the result.
