@@ -694,8 +694,23 @@ def run_b200(args):
     if ctx.rank == 0 and line is not None:
         print(json.dumps(line), flush=True)
     if ctx.world > 1:
+        dbg = os.environ.get('DDG_BENCH_DEBUG')
+        if dbg:
+            print(f'[rank {ctx.rank}] before final barrier', file=sys.stderr, flush=True)
+        torch.cuda.synchronize()
         dist.barrier()
+        if dbg:
+            print(f'[rank {ctx.rank}] after final barrier', file=sys.stderr, flush=True)
+        # The result line is out; tearing NCCL down must not be able to hang the run (seen with collectives captured in CUDA graphs
+        # on a side stream while the graphs were still alive): a watchdog ends the process after 20 s.
+        import gc
+        gc.collect()
+        sys.stdout.flush()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
         dist.destroy_process_group()
+        if dbg:
+            print(f'[rank {ctx.rank}] destroyed', file=sys.stderr, flush=True)
+        os._exit(0)
 
 
 def main():

@@ -660,3 +660,38 @@ extern "C" int ddg_softmax_rows(const float* s, float* p, long rows, int T, int 
   DDG_CHECK_LAUNCH();
   return DDG_OK;
 }
+
+namespace ddg {
+// backward of the row softmax: ds[r][j] = scale * p[r][j] * (dp[r][j] - sum_k p[r][k] dp[r][k]); one warp per row, T <= 1024
+__global__ void __launch_bounds__(256) softmax_rows_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dp, float* __restrict__ ds,
+                                                              long rows, int T, int ld, float scale) {
+  const long row = blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* pr = p + row * ld;
+  const float* gr = dp + row * ld;
+  float* dr = ds + row * ld;
+  float pv[32], gv[32];
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int j = lane + 32 * i;
+    pv[i] = j < T ? pr[j] : 0.f;
+    gv[i] = j < T ? gr[j] : 0.f;
+    dot += pv[i] * gv[i];
+  }
+  dot = warp_sum(dot);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int j = lane + 32 * i;
+    if (j < ld) dr[j] = j < T ? scale * pv[i] * (gv[i] - dot) : 0.f;
+  }
+}
+}  // namespace ddg
+
+extern "C" int ddg_softmax_rows_bwd(const float* p, const float* dp, float* ds, long rows, int T, int ld, float scale, cudaStream_t stream) {
+  if (!p || !dp || !ds || T <= 0 || T > 1024 || ld > 1024 || ld < T) { ddg_set_last_error("softmax_rows_bwd: bad args (T <= 1024)"); return DDG_ERR_ARG; }
+  ddg::softmax_rows_bwd_kernel<<<(int)((rows + 7) / 8), 256, 0, stream>>>(p, dp, ds, rows, T, ld, scale);
+  DDG_CHECK_LAUNCH();
+  return DDG_OK;
+}

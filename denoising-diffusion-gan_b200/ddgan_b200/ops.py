@@ -394,6 +394,27 @@ def spatial_sum(x, act=ACT_NONE, out=None):
     return out
 
 
+def softmax_rows_bwd(p, dp, ds, rows, T, ld, scale):
+    check(lib().ddg_softmax_rows_bwd(ptr(p), ptr(dp), ptr(ds), rows, T, ld, scale, stream()), 'softmax_rows_bwd')
+    return ds
+
+
+def bgemm(a, bsrc, cout, k_real, s_co, s_ci, b_batch_stride, precision=3, out_scale=1.0, out_c=0, elem_offset=0):
+    """Batched GEMM on the tcgen05 conv kernel: out[n] = a[n] @ B[n]^T with a [N, M, Kp] fp32 row-major (Kp % 32 == 0) and
+    B[n][co][ci] = bsrc.flat[elem_offset + n*b_batch_stride + co*s_co + ci*s_ci] for ci < k_real (zero beyond), packed per image.
+    Returns [N, M, out_c or cout] (columns beyond cout are zero when out_c > cout)."""
+    n, m, kp = a.shape
+    assert a.is_contiguous() and kp % KB == 0
+    cw = ConvWeights(cout, [(kp, 1)], a.device, precision=precision, batch=n, m_rows=n * m)
+    cw.pack_segment(0, bsrc, k_real, s_co, s_ci, 0, w_batch_stride=b_batch_stride, elem_offset=elem_offset)
+    oc = out_c or cout
+    out = (torch.zeros if oc != cout else torch.empty)(n, m, oc, device=a.device, dtype=torch.float32)
+    d = build_conv_desc(cw, [conv_src(a, kp, TAPS_1X1, padded=False)], n, 1, m, out, out_mode=OUT_NHWC, out_c=oc, out_scale=out_scale,
+                        batch_rows=m)
+    conv_launch(d)
+    return out
+
+
 def attention_desc(qkv, w3: 'ConvWeights', bias, res, out, stats, n, h, w, c, out_scale, precision=3):
     d = _lib.AttnDesc()
     d.qkv = ptr(qkv); d.w3pack = ptr(w3.buf); d.bias = _addr(bias); d.res = _addr(res); d.out = _addr(out); d.stats = _addr(stats)

@@ -109,11 +109,16 @@ class FlatAdam:
     param group), `ema_state_dict()` / `load_ema_state_dict()` the reference EMA's {name: cpu tensor}, and
     `swap_parameters_with_ema()` is ema.py:57-79 on the arenas."""
 
-    def __init__(self, module, lr, betas=(0.5, 0.999), eps=1e-8, weight_decay=0.0, max_norm=0.0, ema_decay=0.0):
+    def __init__(self, module, lr, betas=(0.5, 0.999), eps=1e-8, weight_decay=0.0, max_norm=0.0, ema_decay=0.0, early=None):
+        """early(name) -> bool: parameters whose gradient is final early in the backward pass are laid out first in the arenas
+        (elements [0, n_early)), so that the data-parallel all-reduce of that contiguous range can overlap the rest of the
+        backward.  Checkpoint I/O goes by name, so the order is invisible outside."""
         from . import _lib
         self._lib = _lib
         self.module = module
         named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+        if early is not None:
+            named = [(n, p) for n, p in named if early(n)] + [(n, p) for n, p in named if not early(n)]
         self.names = [n for n, _ in named]
         self.params = [p for _, p in named]
         dev = self.params[0].device
@@ -126,13 +131,16 @@ class FlatAdam:
         self.v = torch.zeros(n, device=dev)
         off = 0
         self.views = []
-        for p, sz in zip(self.params, sizes):
+        self.n_early = 0
+        for (nme, p), sz in zip(named, sizes):
             pv = self.flat_p[off:off + p.numel()].view_as(p)
             pv.copy_(p.data)
             p.data = pv
             p.grad = self.flat_g[off:off + p.numel()].view_as(p)
             self.views.append((off, p.numel()))
             off += sz
+            if early is not None and early(nme):
+                self.n_early = off
         self.ema = self.flat_p.clone() if ema_decay > 0 else None
         self.state = torch.tensor([0.0, lr], device=dev)
         self.normsq = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -272,7 +280,18 @@ class Trainer:
         if self.fused_optim:
             # grad-norm -> clip -> Adam -> EMA as one flat-arena pass per network
             self.optD = FlatAdam(netD, args.lr_d, betas_d, weight_decay=wd_d, max_norm=clip)
-            self.optG = FlatAdam(netG, args.lr_g, betas_g, weight_decay=wd_g, max_norm=clip, ema_decay=ema_decay)
+            early = None
+            if self.distributed and hasattr(netG, 'cfg'):
+                # up path + head: differentiated first (train_graph.generator_forward fires _grad_ready_hook when the backward
+                # reaches the middle of the network); the AdaGN style / Dense_0 projections get their gradients at the very end
+                from . import train_graph
+                first = train_graph.up_first_idx(netG.cfg)
+
+                def early(name, first=first):
+                    if not name.startswith('all_modules.') or '.style.' in name or 'Dense_0' in name:
+                        return False
+                    return int(name.split('.')[1]) >= first
+            self.optG = FlatAdam(netG, args.lr_g, betas_g, weight_decay=wd_g, max_norm=clip, ema_decay=ema_decay, early=early)
             # the all-reduce is a plain sum; the mean's 1/world rides in the optimiser pass
             self.optD.grad_scale = self.optG.grad_scale = 1.0 / self.world
         else:
@@ -284,6 +303,14 @@ class Trainer:
         self._graphs = None
         self._packs_frozen = False
         self.noise_static = None
+        # data-parallel overlap (fused path): gradient all-reduces run on a side stream
+        self._side = torch.cuda.Stream(device=device) if (self.distributed and self.fused_optim) else None
+        self._g_armed = False
+        self._d_pending = False
+        if self._side is not None and self.optG.n_early > 0:
+            from . import train_graph
+            import weakref
+            train_graph.GRAD_READY_HOOKS[netG] = weakref.WeakMethod(self._g_early_ready)   # no cycle netG -> Trainer -> netG
         self.ema = EMA(netG, ema_decay) if (not self.fused_optim and use_ema) else None
 
     # ---- checkpoint surface of the reference loop (ddgan.py:545-569) ----
@@ -296,10 +323,38 @@ class Trainer:
         elif self.ema is not None:
             self.ema.swap_parameters_with_ema(store_params_in_ema)
 
+    def _g_early_ready(self):
+        """Backward hook (train_graph.generator_forward): the up path and the head have been differentiated -> all-reduce their
+        contiguous range of the gradient arena on the side stream while the down path is still in flight."""
+        if not self._g_armed:
+            return
+        self._g_armed = False
+        self._side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(self._side):
+            dist.all_reduce(self.optG.flat_g[:self.optG.n_early])
+
+    def _d_reduce_async(self):
+        """All D gradients are final after the fake-sample backward: reduce them on the side stream; the optimiser step waits for
+        it just before D is next used (after the generator forward of the G step)."""
+        self._side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(self._side):
+            dist.all_reduce(self.optD.flat_g)
+        self._d_pending = True
+
+    def _d_finish(self):
+        if self._d_pending:
+            torch.cuda.current_stream(self.dev).wait_stream(self._side)
+            self.optD.step()
+            self._d_pending = False
+
     def _reduce_clip_step(self, opt, net, ar_name):
         if self.fused_optim:
             if self.distributed:
-                dist.all_reduce(opt.flat_g)              # the arena IS the bucket: one collective (sum), no copies, no div
+                if opt is self.optG and self._side is not None and opt.n_early > 0:
+                    dist.all_reduce(opt.flat_g[opt.n_early:])            # the rest; the early range is already in flight
+                    torch.cuda.current_stream(self.dev).wait_stream(self._side)
+                else:
+                    dist.all_reduce(opt.flat_g)          # the arena IS the bucket: one collective (sum), no copies, no div
             opt.step()
         else:
             if self.distributed:
@@ -381,7 +436,10 @@ class Trainer:
         errD_fake = F.softplus(output).mean()
         errD_fake.backward()
         errD = errD_real.detach() + errD_fake.detach()
-        self._reduce_clip_step(self.optD, netD, 'arD')
+        if self._side is not None:
+            self._d_reduce_async()       # overlaps the generator forward of the G step; finished by _d_finish() below
+        else:
+            self._reduce_clip_step(self.optD, netD, 'arD')
         # ---------------- G step ----------------
         for p in netD.parameters():
             p.requires_grad = False
@@ -398,9 +456,12 @@ class Trainer:
             z = torch.randn(B, a.nz, device=self.dev)
         x_0_predict = netG(x_tp1.detach(), t, z)
         x_pos_sample = diffusion.sample_posterior(self.pos_coeff, x_0_predict, x_tp1, t, noise=nz.get('n_post_g'))
+        self._d_finish()                 # D's update (ddgan.py:485) must land before D scores the G-step sample
         output = netD(x_pos_sample, t, x_tp1.detach()).view(-1)
         errG = F.softplus(-output).mean()
+        self._g_armed = self._side is not None
         errG.backward()
+        self._g_armed = False
         self._reduce_clip_step(self.optG, netG, 'arG')
         if self.ema is not None:
             self.ema.step()

@@ -100,6 +100,11 @@ def freeze_packs(mod):
 
 _CUR_PACKS = [None]
 
+# module -> callable fired in the backward pass when the up path + head have been differentiated (see generator_forward).  Kept
+# outside the module so that copy.deepcopy / pickling of the network never drags a Trainer along.
+import weakref
+GRAD_READY_HOOKS = weakref.WeakKeyDictionary()
+
 
 def conv_spec(w_shape, taps, n, hout, wout, cpad_in, s_co, s_ci, s_tap, cout, cin, hp=None, wp=None, out_nchw=False, prec=3, out_scale=1.0):
     return SimpleNamespace(w_shape=tuple(w_shape), taps=list(taps), n=n, hout=hout, wout=wout, hp=hp or hout + 2,
@@ -586,6 +591,67 @@ def gn_act(x, h, w, groups, act, gamma=None, beta=None, style=None, off=0, hub=N
     return GnActFn.apply(x, gamma, beta, g)
 
 
+def up_first_idx(cfg):
+    """all_modules index of the first up-path block (same walk as generator_forward): the modules from there on are the ones
+    differentiated first in the backward pass."""
+    cfg = arch.normalize_config(cfg)
+    rest = arch.ncsnpp_modules(cfg)[3:]
+    i, cur, nres = 0, cfg.image_size, len(cfg.ch_mult)
+    for lvl in range(nres):
+        for _ in range(cfg.num_res_blocks):
+            i += 1
+            if cur in cfg.attn_resolutions:
+                i += 1
+        if lvl != nres - 1:
+            i += 1
+            if cfg.progressive_input == 'residual':
+                i += 1
+            cur //= 2
+    return rest[i + 3]['idx']
+
+
+class AttnCoreFn(Function):
+    """o = softmax(q k^T / sqrt(C)) v per sample (layerspp.py:115-119) on this library's kernels, forward and backward: batched
+    tcgen05 GEMMs with per-image packed operands (ops.bgemm), ddg_softmax_rows and its backward.  q, k, v: [N, T, C] fp32.
+    First-order only (the generator never sits under the R1 double backward)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, prec):
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        n, t, c = q.shape
+        tp = ops.pad_c(t)
+        scale = float(c) ** -0.5
+        s = ops.bgemm(q, k, t, c, c, 1, t * c, precision=prec, out_scale=scale, out_c=tp)          # [N, T, Tp] logits
+        p = torch.empty_like(s)
+        ops.softmax_rows(s, p, n * t, t, tp, tp)
+        o = ops.bgemm(p, v, c, t, 1, c, t * c, precision=prec)                                       # B[c][s] = v[s][c]
+        ctx.save_for_backward(q, k, v, p)
+        ctx.cfg = (prec, scale, tp)
+        return o
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, do):
+        q, k, v, p = ctx.saved_tensors
+        prec, scale, tp = ctx.cfg
+        n, t, c = q.shape
+        do = do.contiguous()
+
+        def transposed(m):            # [N, T, Tp] (valid [:, :, :T]) -> its per-image transpose, same padding
+            if tp == t:
+                return m.transpose(1, 2).contiguous()
+            out = torch.zeros_like(m)
+            out[:, :, :t] = m[:, :, :t].transpose(1, 2)
+            return out
+        dv = ops.bgemm(transposed(p), do, c, t, 1, c, t * c, precision=prec)                        # dV[s][c] = sum_t P[t][s] dO[t][c]
+        dp = ops.bgemm(do, v, t, c, c, 1, t * c, precision=prec, out_c=tp)                           # dP[t][s] = sum_c dO[t][c] V[s][c]
+        ds = torch.empty_like(dp)
+        ops.softmax_rows_bwd(p, dp, ds, n * t, t, tp, scale)                                         # includes the 1/sqrt(C)
+        dq = ops.bgemm(ds, k, c, t, 1, c, t * c, precision=prec)                                     # dQ[t][c] = sum_s dS[t][s] K[s][c]
+        dk = ops.bgemm(transposed(ds), q, c, t, 1, c, t * c, precision=prec)                         # dK[s][c] = sum_t dS[t][s] Q[t][c]
+        return dq, dk, dv, None
+
+
 def _tc_linear(n, k, j):
     """Large projections (the batched AdaGN style / Dense_0 GEMMs) go to the tcgen05 kernels; small ones stay on the SIMT kernel."""
     return j >= 1024 and k % 32 == 0 and n % 8 == 0 and j % 32 == 0
@@ -762,8 +828,7 @@ def generator_forward(mod, x, time_cond, z):
         q = _interior(nin(g, P[pn + 'NIN_0.W'], P[pn + 'NIN_0.b'], N, h, w, prec)).reshape(N, h * w, c)
         k = _interior(nin(g, P[pn + 'NIN_1.W'], P[pn + 'NIN_1.b'], N, h, w, prec)).reshape(N, h * w, c)
         v = _interior(nin(g, P[pn + 'NIN_2.W'], P[pn + 'NIN_2.b'], N, h, w, prec)).reshape(N, h * w, c)
-        a = torch.softmax(torch.bmm(q, k.transpose(1, 2)) * (int(c) ** (-0.5)), dim=-1)
-        o = torch.bmm(a, v).reshape(N, h, w, c)
+        o = AttnCoreFn.apply(q, k, v, prec).reshape(N, h, w, c)
         o = F.pad(o, (0, 0, 1, 1, 1, 1))
         return nin(o, P[pn + 'NIN_3.W'], P[pn + 'NIN_3.b'], N, h, w, prec, res=t, out_scale=RSQRT2 if cfg.skip_rescale else 1.0)
 
@@ -804,6 +869,13 @@ def generator_forward(mod, x, time_cond, z):
     h, _, _ = resblock(rest[i], h, cur, cur); i += 1
     h = attn(rest[i], h, cur, cur); i += 1
     h, _, _ = resblock(rest[i], h, cur, cur); i += 1
+    # Data-parallel overlap point: when the backward pass gets back here, every weight gradient of the up path and the head (module
+    # index >= up_first_idx(cfg), about 60 % of the parameters) has been enqueued -- train.Trainer all-reduces that part of the
+    # gradient arena on a side stream while the down path is still being differentiated.
+    hook = GRAD_READY_HOOKS.get(mod)
+    hook = hook() if hook is not None else None          # WeakMethod: the Trainer may be gone
+    if hook is not None and torch.is_grad_enabled() and h.requires_grad:
+        h.register_hook(lambda g, hook=hook: hook())
     for lvl in reversed(range(nres)):
         for _ in range(cfg.num_res_blocks + 1):
             skip, _ = hs.pop()

@@ -116,6 +116,8 @@ int ddg_spatial_sum(const float* x, float* out, int N, int H, int W, int C, int 
 int ddg_zero_border(float* buf, int N, int H, int W, int C, cudaStream_t stream);
 /* row softmax of the attention logits (layerspp.py:116-118): p[r][0:T] = softmax(s[r][0:T]), p[r][T:ldp] = 0 */
 int ddg_softmax_rows(const float* s, float* p, long rows, int T, int lds, int ldp, cudaStream_t stream);
+/* its backward (training path of the attention core): ds[r][j] = scale * p[r][j] * (dp[r][j] - sum_k p[r][k] dp[r][k]), ds[r][T:ld] = 0 */
+int ddg_softmax_rows_bwd(const float* p, const float* dp, float* ds, long rows, int T, int ld, float scale, cudaStream_t stream);
 
 /* ---- implicit-GEMM convolution on tcgen05 / TMEM (replaces nn.Conv2d -> cuDNN: layers.py:114-138,
  *      dense_layer.py:73-80, NIN layers.py:489-512, up_or_down_sampling.py:56,183) -------------------------------- */

@@ -248,3 +248,20 @@ def test_flat_adam_matches_torch_clip_adam_ema():
     sd = fa.ema_state_dict(net_a)
     for (n, _), e in zip(net_a.named_parameters(), ema):
         assert O.rel_l2(sd[n].cpu(), e.cpu()) < 1e-6
+
+
+@pytest.mark.parametrize('n,t,c', [(3, 256, 256), (4, 16, 64), (2, 64, 128)])
+def test_attention_core_function_grads(n, t, c):
+    """AttnCoreFn (training path of layerspp.py:115-119 on this library's GEMM / softmax kernels) against torch autograd."""
+    from ddgan_b200 import train_graph as TG
+    q, k, v = seeded((n, t, c), 31), seeded((n, t, c), 32), seeded((n, t, c), 33)
+    gy = seeded((n, t, c), 34)
+    qr, kr, vr = [x.clone().requires_grad_(True) for x in (q, k, v)]
+    ref = torch.bmm(torch.softmax(torch.bmm(qr, kr.transpose(1, 2)) * (c ** -0.5), dim=-1), vr)
+    g_ref = torch.autograd.grad((ref * gy).sum(), (qr, kr, vr))
+    qd, kd, vd = [x.to(DEV).requires_grad_(True) for x in (q, k, v)]
+    o = TG.AttnCoreFn.apply(qd, kd, vd, 3)
+    assert O.rel_l2(o.detach().cpu(), ref.detach()) < 2e-5
+    g = torch.autograd.grad((o * gy.to(DEV)).sum(), (qd, kd, vd))
+    for a, b_ in zip(g, g_ref):
+        assert O.rel_l2(a.cpu(), b_) < 5e-5
