@@ -283,43 +283,94 @@ __global__ void __launch_bounds__(kGnThreads) groupnorm_bwd_kernel(const float* 
                                                                    float* __restrict__ dx, float* __restrict__ dgamma,
                                                                    float* __restrict__ dbeta, int C, int HW, int G, int per_sample,
                                                                    int act) {
-  __shared__ float red[32];
+  // One CTA per (n, group) slab.  Pass 1 sweeps the slab channel by channel with 128-bit loads; every warp leaves its partial
+  // {sum du*xhat, sum du} per channel in shared memory and ONE barrier later the first threads finish the per-channel sums (the
+  // first version paid six barriers per channel).  Pass 2 re-reads the slab (it is L2-resident: <= a few hundred KB) for dx.
+  __shared__ float part[kGnMaxCpg][2][kGnThreads / 32];
+  __shared__ float chan[kGnMaxCpg][4];      // per channel: a = sum du*xhat, b = sum du, gamma, beta
+  __shared__ float msum[2];
   const int ng = blockIdx.x;
   const int n = ng / G, g = ng - n * G;
   const int cpg = C / G;
   const long len = (long)cpg * HW;
   const size_t base = ((size_t)n * C + (size_t)g * cpg) * HW;
   const float mean = mean_in[ng], rstd = rstd_in[ng];
-  // pass 1: per-channel sums of du and du*xhat (needed for dgamma/dbeta and for the group means)
-  float sum1 = 0.f, sum2 = 0.f;  // sum dxhat, sum dxhat*xhat over the group
-  for (int cl = 0; cl < cpg; ++cl) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool vec = (HW % 4 == 0) && ((base % 4) == 0);
+  for (int cl = threadIdx.x; cl < cpg; cl += blockDim.x) {
     const int c = g * cpg + cl;
     float ga = 1.f, be = 0.f;
     if (gamma) { ga = per_sample ? gamma[(size_t)n * C + c] : gamma[c]; be = per_sample ? beta[(size_t)n * C + c] : beta[c]; }
-    float a = 0.f, b = 0.f;
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-      const float xh = (x[base + (size_t)cl * HW + i] - mean) * rstd;
-      const float du = dy[base + (size_t)cl * HW + i] * act_grad(fmaf(ga, xh, be), act);
-      a += du * xh;
-      b += du;
-    }
-    a = block_sum(a, red);
-    b = block_sum(b, red);
-    if (threadIdx.x == 0) {
-      if (dgamma) dgamma[(size_t)n * C + c] = a;
-      if (dbeta) dbeta[(size_t)n * C + c] = b;
-    }
-    sum1 += b * ga;
-    sum2 += a * ga;
+    chan[cl][2] = ga; chan[cl][3] = be;
   }
-  const float m1 = sum1 / (float)len, m2 = sum2 / (float)len;
-  for (long i = threadIdx.x; i < len; i += blockDim.x) {
-    const int c = g * cpg + (int)(i / HW);
-    float ga = 1.f, be = 0.f;
-    if (gamma) { ga = per_sample ? gamma[(size_t)n * C + c] : gamma[c]; be = per_sample ? beta[(size_t)n * C + c] : beta[c]; }
-    const float xh = (x[base + i] - mean) * rstd;
-    const float du = dy[base + i] * act_grad(fmaf(ga, xh, be), act);
-    dx[base + i] = rstd * (du * ga - m1 - xh * m2);
+  __syncthreads();
+  for (int cl = 0; cl < cpg; ++cl) {
+    const float ga = chan[cl][2], be = chan[cl][3];
+    const float* xc = x + base + (size_t)cl * HW;
+    const float* gc = dy + base + (size_t)cl * HW;
+    float a = 0.f, b = 0.f;
+    if (vec) {
+      for (int i = threadIdx.x; i < HW / 4; i += blockDim.x) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(xc) + i);
+        const float4 gv = ldg_stream(reinterpret_cast<const float4*>(gc) + i);
+        float xh, du;
+        xh = (xv.x - mean) * rstd; du = gv.x * act_grad(fmaf(ga, xh, be), act); a += du * xh; b += du;
+        xh = (xv.y - mean) * rstd; du = gv.y * act_grad(fmaf(ga, xh, be), act); a += du * xh; b += du;
+        xh = (xv.z - mean) * rstd; du = gv.z * act_grad(fmaf(ga, xh, be), act); a += du * xh; b += du;
+        xh = (xv.w - mean) * rstd; du = gv.w * act_grad(fmaf(ga, xh, be), act); a += du * xh; b += du;
+      }
+    } else {
+      for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+        const float xh = (xc[i] - mean) * rstd;
+        const float du = gc[i] * act_grad(fmaf(ga, xh, be), act);
+        a += du * xh;
+        b += du;
+      }
+    }
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) { part[cl][0][warp] = a; part[cl][1][warp] = b; }
+  }
+  __syncthreads();
+  for (int cl = threadIdx.x; cl < cpg; cl += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < kGnThreads / 32; ++w) { a += part[cl][0][w]; b += part[cl][1][w]; }
+    chan[cl][0] = a; chan[cl][1] = b;
+    const int c = g * cpg + cl;
+    if (dgamma) dgamma[(size_t)n * C + c] = a;
+    if (dbeta) dbeta[(size_t)n * C + c] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int cl = 0; cl < cpg; ++cl) { s1 += chan[cl][1] * chan[cl][2]; s2 += chan[cl][0] * chan[cl][2]; }
+    msum[0] = s1 / (float)len; msum[1] = s2 / (float)len;
+  }
+  __syncthreads();
+  const float m1 = msum[0], m2 = msum[1];
+  if (vec) {
+    const int hw4 = HW / 4;
+    for (long i = threadIdx.x; i < len / 4; i += blockDim.x) {
+      const int cl = (int)(i / hw4);
+      const float ga = chan[cl][2], be = chan[cl][3];
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + base) + i);
+      const float4 gv = ldg_stream(reinterpret_cast<const float4*>(dy + base) + i);
+      float4 o;
+      float xh, du;
+      xh = (xv.x - mean) * rstd; du = gv.x * act_grad(fmaf(ga, xh, be), act); o.x = rstd * (du * ga - m1 - xh * m2);
+      xh = (xv.y - mean) * rstd; du = gv.y * act_grad(fmaf(ga, xh, be), act); o.y = rstd * (du * ga - m1 - xh * m2);
+      xh = (xv.z - mean) * rstd; du = gv.z * act_grad(fmaf(ga, xh, be), act); o.z = rstd * (du * ga - m1 - xh * m2);
+      xh = (xv.w - mean) * rstd; du = gv.w * act_grad(fmaf(ga, xh, be), act); o.w = rstd * (du * ga - m1 - xh * m2);
+      stg_stream(reinterpret_cast<float4*>(dx + base) + i, o);
+    }
+  } else {
+    for (long i = threadIdx.x; i < len; i += blockDim.x) {
+      const int cl = (int)(i / HW);
+      const float ga = chan[cl][2], be = chan[cl][3];
+      const float xh = (x[base + i] - mean) * rstd;
+      const float du = dy[base + i] * act_grad(fmaf(ga, xh, be), act);
+      dx[base + i] = rstd * (du * ga - m1 - xh * m2);
+    }
   }
 }
 

@@ -67,6 +67,8 @@ _SIGNATURES = {
     'ddg_upfirdn2d_out_size': ([_I] * 6, _I),
     'ddg_fused_bias_act': ([_P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _P], _I),
     'ddg_channel_sum': ([_P, _P, _I, _I, _I, _P], _I),
+    'ddg_upfirdn2d_lp': ([_P, _P, _P, _L] + [_I] * 9 + [_P], _I),
+    'ddg_fused_bias_act_lp': ([_P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _I, _P], _I),
     'ddg_groupnorm_fwd': ([_P] * 6 + [_I] * 4 + [_F, _I, _I, _P], _I),
     'ddg_groupnorm_bwd': ([_P] * 9 + [_I] * 6 + [_P], _I),
     'ddg_timestep_embedding': ([_P, _P, _I, _I, _F, _P], _I),
@@ -150,6 +152,9 @@ def ptr(t):
 
 def stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+LP_DTYPES = {torch.float16: 1, torch.bfloat16: 2}
 
 
 def require_cuda_f32(*tensors):

@@ -31,7 +31,22 @@ def pad_c(c: int, m: int = KB) -> int:
 # score_sde.op surface primitives
 # ---------------------------------------------------------------------------------------------------------
 def upfirdn2d_raw(x: torch.Tensor, k: torch.Tensor, up_x, up_y, down_x, down_y, px0, px1, py0, py1) -> torch.Tensor:
-    """x [planes, H, W] -> [planes, H', W'] (upfirdn2d.cpp:20-31 argument order)."""
+    """x [planes, H, W] -> [planes, H', W'] (upfirdn2d.cpp:20-31 argument order).  fp16 / bf16 inputs go to the 16-bit kernels
+    (same up / down / pad on both axes, as the Python surface always passes)."""
+    if x.dtype in _lib.LP_DTYPES:
+        if not x.is_cuda:
+            raise RuntimeError('ddgan_b200 ops run on CUDA tensors only (no CPU fallback)')
+        if not (up_x == up_y and down_x == down_y and px0 == py0 and px1 == py1):
+            raise NotImplementedError('16-bit upfirdn2d: up / down / pad must be the same on both axes')
+        x = x.contiguous()
+        k = k.to(torch.float32).contiguous()
+        planes, in_h, in_w = x.shape
+        kh, kw = k.shape
+        out = torch.empty(planes, (in_h * up_y + py0 + py1 - kh) // down_y + 1, (in_w * up_x + px0 + px1 - kw) // down_x + 1,
+                          device=x.device, dtype=x.dtype)
+        check(lib().ddg_upfirdn2d_lp(ptr(x), ptr(k), ptr(out), planes, in_h, in_w, kh, kw, up_x, down_x, px0, px1,
+                                     _lib.LP_DTYPES[x.dtype], stream()), 'upfirdn2d_lp')
+        return out
     require_cuda_f32(x, k)
     x = x.contiguous()
     k = k.contiguous()
@@ -46,7 +61,20 @@ def upfirdn2d_raw(x: torch.Tensor, k: torch.Tensor, up_x, up_y, down_x, down_y, 
 
 
 def fused_bias_act(x, b, ref, act: int, grad: int, alpha: float, scale: float) -> torch.Tensor:
-    """fused_bias_act.cpp:18-28; b / ref may be None or 0-element ('absent')."""
+    """fused_bias_act.cpp:18-28; b / ref may be None or 0-element ('absent').  fp16 / bf16 x (and ref) use the 16-bit kernel."""
+    if x.dtype in _lib.LP_DTYPES:
+        if not x.is_cuda:
+            raise RuntimeError('ddgan_b200 ops run on CUDA tensors only (no CPU fallback)')
+        x = x.contiguous()
+        b = None if (b is None or b.numel() == 0) else b.to(torch.float32).contiguous()
+        ref = None if (ref is None or ref.numel() == 0) else ref.to(x.dtype).contiguous()
+        y = torch.empty_like(x)
+        step_b = 1
+        for d in x.shape[2:]:
+            step_b *= d
+        check(lib().ddg_fused_bias_act_lp(ptr(x), ptr(b), ptr(ref), ptr(y), x.numel(), step_b, b.numel() if b is not None else 1, act,
+                                          grad, alpha, scale, _lib.LP_DTYPES[x.dtype], stream()), 'fused_bias_act_lp')
+        return y
     require_cuda_f32(x)
     x = x.contiguous()
     b = None if (b is None or b.numel() == 0) else b.contiguous()

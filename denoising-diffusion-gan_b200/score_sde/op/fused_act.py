@@ -16,7 +16,8 @@ class FusedLeakyReLUFunctionBackward(Function):
         ctx.save_for_backward(out)
         ctx.negative_slope, ctx.scale = negative_slope, scale
         grad_input = ops.fused_bias_act(grad_output, None, out, 3, 1, negative_slope, scale)
-        grad_bias = ops.channel_sum(grad_input) if grad_input.ndim >= 2 else grad_input.sum(0)
+        gsum = grad_input if grad_input.dtype == torch.float32 else grad_input.float()   # 16-bit gradients: reduce in fp32
+        grad_bias = ops.channel_sum(gsum) if gsum.ndim >= 2 else gsum.sum(0)
         return grad_input, grad_bias
 
     @staticmethod

@@ -39,6 +39,13 @@ int ddg_upfirdn2d_out_size(int in_size, int up, int down, int pad0, int pad1, in
  * ref > 0; grad=2 -> 0.  act=1 linear.  b / ref may be NULL ("empty tensor" in the reference). */
 int ddg_fused_bias_act(const float* x, const float* b, const float* ref, float* y, long n, int step_b, int size_b,
                        int act, int grad, float alpha, float scale, cudaStream_t stream);
+/* 16-bit I/O variants of the two operators (the reference dispatches over AT_DISPATCH_FLOATING_TYPES_AND_HALF,
+ * upfirdn2d_kernel.cu:313 / fused_bias_act_kernel.cu:79): dtype 1 = fp16, 2 = bf16 for x / ref / out; taps and bias stay fp32,
+ * accumulation is fp32.  up / down / pad apply to both axes as in the Python surface (upfirdn2d.py:153-164). */
+int ddg_upfirdn2d_lp(const void* x, const float* k, void* out, long planes, int in_h, int in_w, int kh, int kw, int up, int down,
+                     int pad0, int pad1, int dtype, cudaStream_t stream);
+int ddg_fused_bias_act_lp(const void* x, const float* b, const void* ref, void* y, long n, int step_b, int size_b, int act, int grad,
+                          float alpha, float scale, int dtype, cudaStream_t stream);
 /* grad_bias of FusedLeakyReLUFunctionBackward (fused_act.py:42-47): out[c] = sum over n, spatial of g[n][c][...] */
 int ddg_channel_sum(const float* g, float* out, int N, int C, int inner, cudaStream_t stream);
 

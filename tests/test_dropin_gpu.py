@@ -109,3 +109,37 @@ def test_model_classes_keep_reference_constructor_forward_and_state_dict(golden)
     ref = O.discriminator_forward(sdd, xa, td, xb, 32)
     assert tuple(d.shape) == (4, 1) and O.rel_l2(d.cpu(), ref) < 1e-4
     assert Discriminator_large is not None
+
+
+@pytest.mark.parametrize('dtype,tol', [(torch.bfloat16, 1e-2), (torch.float16, 2e-3)])
+def test_sixteen_bit_operator_surface(dtype, tol):
+    """The reference dispatches both operators over fp16 as well (upfirdn2d_kernel.cu:313, fused_bias_act_kernel.cu:79); here fp16
+    and bf16 tensors run 16-bit kernels with fp32 accumulation.  Expected values: the fp32 path on the upcast inputs; stated
+    tolerance = rounding of the 16-bit output (bf16 2^-9, fp16 2^-11 relative), forward and first-order gradient."""
+    from score_sde.op import upfirdn2d, fused_leaky_relu
+    from score_sde.models.up_or_down_sampling import upsample_2d, downsample_2d
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(4, 32, 16, 16, generator=g).to(DEV)
+    xl = x.to(dtype)
+    for fn in (lambda t: upsample_2d(t, (1, 3, 3, 1), factor=2), lambda t: downsample_2d(t, (1, 3, 3, 1), factor=2)):
+        ref = fn(xl.float())
+        got = fn(xl)
+        assert got.dtype == dtype and got.shape == ref.shape
+        assert float((got.float() - ref).norm() / ref.norm()) < tol
+    k = torch.tensor([[1., 2., 1.], [2., 4., 2.], [1., 2., 1.]], device=DEV) / 16
+    xr = xl.clone().requires_grad_(True)
+    xf = xl.float().requires_grad_(True)
+    y = upfirdn2d(xr, k, up=1, down=1, pad=(1, 1))
+    yf = upfirdn2d(xf, k, up=1, down=1, pad=(1, 1))
+    gy = torch.randn(yf.shape, generator=g).to(DEV)
+    y.backward(gy.to(dtype)); yf.backward(gy.to(dtype).float())
+    assert float((xr.grad.float() - xf.grad).norm() / xf.grad.norm()) < tol
+    b = torch.randn(32, generator=g).to(DEV)
+    xr = xl.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+    xf = xl.float().requires_grad_(True); bf = b.clone().requires_grad_(True)
+    y = fused_leaky_relu(xr, br)
+    yf = fused_leaky_relu(xf, bf)
+    assert y.dtype == dtype and float((y.float() - yf).norm() / yf.norm()) < tol
+    y.backward(gy.to(dtype)); yf.backward(gy.to(dtype).float())
+    assert float((xr.grad.float() - xf.grad).norm() / xf.grad.norm()) < tol
+    assert float((br.grad - bf.grad).norm() / bf.grad.norm()) < tol
