@@ -214,6 +214,7 @@ struct ConvDev {
   long w_batch_stride;         // bytes between the packed B operands of consecutive batches
   int nsa;                     // A-operand ring depth (2..4 stages, whatever the shared-memory budget allows)
   int tma_pitch;               // chunk pitch of a TMA-written A plane: window rows * 16 bytes, dense (producer planes are padded)
+  int zero_border;             // PNHWC output into a fresh (uninitialised) buffer: edge pixels also clear the adjacent frame
   void* out_planes;            // optional pre-split copy of the PNHWC output (see ddg_conv_desc.out_planes)
   long out_plane_bytes;
   alignas(64) CUtensorMap tmap[DDG_CONV_MAX_SRC][2];   // hi / lo plane of every TMA-fed source
@@ -423,6 +424,30 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
               float4* o4 = reinterpret_cast<float4*>(p.out + obase + col0);
 #pragma unroll
               for (int j = 0; j < CW / 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (p.zero_border && p.out_mode == 0) {
+                // fresh output buffer (training path): the threads that own the edge pixels clear the one-pixel frame next to them,
+                // for their channel chunk -- every frame pixel has exactly one interior neighbour along its normal (corners: the
+                // corner pixel), so the frame is covered once per chunk and no separate border-clearing launch is needed.
+                // Kept as a compact run-time loop: it runs for edge pixels only and must not bloat the epilogue.
+                const int eL = (w == 0), eR = (w == p.Wout - 1), eT = (h == 0), eB = (h == p.Hout - 1);
+                if (eL | eR | eT | eB) {
+                  const long rowp = (long)(p.Wout + 2) * p.out_C;
+                  float* ctr = p.out + obase + col0;
+#pragma unroll 1
+                  for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll 1
+                    for (int dx = -1; dx <= 1; ++dx) {
+                      const bool oky = dy == 0 || (dy < 0 ? eT : eB);
+                      const bool okx = dx == 0 || (dx < 0 ? eL : eR);
+                      if ((dy | dx) != 0 && oky && okx) {
+                        float4* q = reinterpret_cast<float4*>(ctr + dy * rowp + dx * p.out_C);
+#pragma unroll 1
+                        for (int j = 0; j < CW / 4; ++j) q[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                      }
+                    }
+                  }
+                }
+              }
               if (p.out_planes != nullptr && full && p.out_mode == 0) {
                 // the same values once more as bf16 hi / lo planes [n][chunk][h+1][w+1][8]: consumers that take this tensor without a
                 // prologue (1x1 skip convs) fetch them with the TMA engine instead of converting fp32 in their producer warps
@@ -1255,6 +1280,7 @@ extern "C" int ddg_conv2d_fwd(const ddg_conv_desc* c, cudaStream_t stream) {
   }
   g_last_info[4] = 0;
   for (int s = 0; s < c->nsrc; ++s) g_last_info[4] += d.src[s].tma;
+  d.zero_border = (c->out_mode == 0 && c->zero_border) ? 1 : 0;
   d.out_planes = (c->out_mode == 0) ? c->out_planes : nullptr;
   d.out_plane_bytes = ddg_planes_bytes(d.N, d.Hout, d.Wout, d.out_C);
 

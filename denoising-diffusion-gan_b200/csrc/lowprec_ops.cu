@@ -70,9 +70,8 @@ __global__ void __launch_bounds__(256) upfirdn2d_lp_kernel(const T* __restrict__
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
     const int base_y = oy * down - p.pad0;
-#pragma unroll
-    for (int i = 0; i < (KS ? KS : 16); ++i) {
-      if (i >= kh) break;
+#pragma unroll(KS ? KS : 1)
+    for (int i = 0; i < kh; ++i) {
       const int a = base_y + i;
       if (a < 0 || (a % up) != 0) continue;
       const int iy = a / up;
@@ -81,9 +80,8 @@ __global__ void __launch_bounds__(256) upfirdn2d_lp_kernel(const T* __restrict__
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         const int base_x = (xv * VEC + v) * down - p.pad0;
-#pragma unroll
-        for (int j = 0; j < (KS ? KS : 16); ++j) {
-          if (j >= kw) break;
+#pragma unroll(KS ? KS : 1)
+        for (int j = 0; j < kw; ++j) {
           const int b = base_x + j;
           if (b < 0 || (b % up) != 0) continue;
           const int ix = b / up;

@@ -8,6 +8,23 @@
 
 namespace ddg {
 
+// The thread that writes interior pixel (h, w) of a fresh PNHWC buffer also clears the frame pixels next to it (4 channels at c0):
+// every frame pixel has exactly one such neighbour, so the one-pixel border ends up zero without a separate launch.
+__device__ __forceinline__ void clear_frame(float* ctr, int h, int w, int H, int W, int C) {
+  const bool eL = (w == 0), eR = (w == W - 1), eT = (h == 0), eB = (h == H - 1);
+  if (!(eL | eR | eT | eB)) return;
+  const long rowp = (long)(W + 2) * C;
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (eL) *reinterpret_cast<float4*>(ctr - C) = z;
+  if (eR) *reinterpret_cast<float4*>(ctr + C) = z;
+  if (eT) *reinterpret_cast<float4*>(ctr - rowp) = z;
+  if (eB) *reinterpret_cast<float4*>(ctr + rowp) = z;
+  if (eT && eL) *reinterpret_cast<float4*>(ctr - rowp - C) = z;
+  if (eT && eR) *reinterpret_cast<float4*>(ctr - rowp + C) = z;
+  if (eB && eL) *reinterpret_cast<float4*>(ctr + rowp - C) = z;
+  if (eB && eR) *reinterpret_cast<float4*>(ctr + rowp + C) = z;
+}
+
 __device__ __forceinline__ float act_d(float u, int act) {
   if (act == ACT_SILU) { const float s = 1.f / (1.f + __expf(-u)); return s * (1.f + u * (1.f - s)); }
   if (act == ACT_LEAKY) return u > 0.f ? 1.f : 0.2f;
@@ -34,6 +51,7 @@ __global__ void __launch_bounds__(256) affine_act_fwd_kernel(const float* __rest
     }
     v.x = apply_act(v.x, act); v.y = apply_act(v.y, act); v.z = apply_act(v.z, act); v.w = apply_act(v.w, act);
     stg_stream(reinterpret_cast<float4*>(y + off), v);
+    clear_frame(y + off, h, w, H, W, C);
   }
 }
 
@@ -145,6 +163,7 @@ __global__ void __launch_bounds__(256) gn_bwd_dx_kernel(const float* __restrict_
     o.z = g.z * act_d(fmaf(v.z, s.z, t.z), act) * s.z + g1.x + 2.f * v.z * g1.y;
     o.w = g.w * act_d(fmaf(v.w, s.w, t.w), act) * s.w + g1.z + 2.f * v.w * g1.w;
     stg_stream(reinterpret_cast<float4*>(dx + off), o);
+    clear_frame(dx + off, h, w, H, W, C);
   }
 }
 

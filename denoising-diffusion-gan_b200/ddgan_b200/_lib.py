@@ -28,7 +28,7 @@ class ConvDesc(C.Structure):
                 ('bias', C.c_void_p), ('addvec', C.c_void_p), ('addvec_stride', C.c_int), ('res', C.c_void_p),
                 ('out_scale', C.c_float), ('out_act', C.c_int), ('out', C.c_void_p), ('out_mode', C.c_int),
                 ('out_C', C.c_int), ('stats', C.c_void_p), ('precision', C.c_int), ('msub', C.c_int),
-                ('force_linear', C.c_int), ('debug_prof', C.c_void_p), ('batch_rows', C.c_int), ('out_planes', C.c_void_p)]
+                ('force_linear', C.c_int), ('debug_prof', C.c_void_p), ('batch_rows', C.c_int), ('zero_border', C.c_int), ('out_planes', C.c_void_p)]
 
 
 class WgradDesc(C.Structure):

@@ -204,21 +204,23 @@ def sample_posterior(x0, x_t, noise, t, coef1, coef2, logvar, out=None):
 _POISON = bool(os.environ.get('DDG_POISON_ALLOC'))   # test aid: NaN-fill fresh interiors to catch kernels that skip elements
 
 
-def alloc_pnhwc(n, h, w, c, device, full=True) -> torch.Tensor:
+def alloc_pnhwc(n, h, w, c, device, full=True, border=True) -> torch.Tensor:
     """[N, H+2, W+2, C] with a zero border.  full=False: only the frame is cleared (for producers that write every interior
-    element and channel); full=True zero-fills the whole buffer."""
+    element and channel); full=True zero-fills the whole buffer; border=False: nothing is cleared -- the producing kernel
+    writes the frame itself (conv with zero_border=1, ddg_affine_act_fwd, ddg_gn_bwd_dx)."""
     if full or c % 4 != 0:
         return torch.zeros(n, h + 2, w + 2, c, device=device, dtype=torch.float32)
     out = torch.empty(n, h + 2, w + 2, c, device=device, dtype=torch.float32)
     if _POISON:
         out.fill_(float('nan'))
-    check(lib().ddg_zero_border(ptr(out), n, h, w, c, stream()), 'zero_border')
+    if border:
+        check(lib().ddg_zero_border(ptr(out), n, h, w, c, stream()), 'zero_border')
     return out
 
 
-def empty_like_pnhwc(x) -> torch.Tensor:
+def empty_like_pnhwc(x, border=True) -> torch.Tensor:
     n, hp, wp, c = x.shape
-    return alloc_pnhwc(n, hp - 2, wp - 2, c, x.device, full=False)
+    return alloc_pnhwc(n, hp - 2, wp - 2, c, x.device, full=False, border=border)
 
 
 def to_pnhwc(a, b=None, cpad=None, out=None, scale=1.0, shift=0.0):
@@ -281,7 +283,7 @@ def fir_pnhwc(x, mode, out, scale=None, shift=None, act=ACT_NONE, gain=1.0):
 def affine_act_fwd(x, scale, shift, act, out=None):
     n, hp, wp, c = x.shape
     if out is None:
-        out = empty_like_pnhwc(x)
+        out = empty_like_pnhwc(x, border=False)        # the kernel clears the frame itself
     check(lib().ddg_affine_act_fwd(ptr(x), ptr(scale), ptr(shift), ptr(out), n, hp - 2, wp - 2, c, act, stream()), 'affine_act_fwd')
     return out
 
@@ -305,7 +307,7 @@ def gn_bwd_coeffs(stats, sums, gamma, gb_stride, per_sample, g12, dgamma, dbeta,
 
 def gn_bwd_dx(x, dy, scale, shift, g12, act):
     n, hp, wp, c = x.shape
-    dx = empty_like_pnhwc(x)
+    dx = empty_like_pnhwc(x, border=False)             # the kernel clears the frame itself
     check(lib().ddg_gn_bwd_dx(ptr(x), ptr(dy), ptr(scale), ptr(shift), ptr(g12), ptr(dx), n, hp - 2, wp - 2, c, act, stream()), 'gn_bwd_dx')
     return dx
 
@@ -602,7 +604,7 @@ def _addr(v):
 
 def build_conv_desc(weights: ConvWeights, srcs, n, hout, wout, out, out_mode=OUT_PNHWC, hp=None, wp=None, bias=None, addvec=None,
                     addvec_stride=0, res=None, out_scale=1.0, out_act=ACT_NONE, out_c=0, stats=None, msub=0, batch_rows=0, prof=None, force_linear=0,
-                    out_planes=None) -> ConvDesc:
+                    out_planes=None, zero_border=0) -> ConvDesc:
     d = ConvDesc()
     d.nsrc = len(srcs)
     for i, s in enumerate(srcs):
@@ -631,6 +633,7 @@ def build_conv_desc(weights: ConvWeights, srcs, n, hout, wout, out, out_mode=OUT
     d.debug_prof = _addr(prof)
     d.force_linear = force_linear
     d.out_planes = _addr(out_planes)
+    d.zero_border = int(zero_border)
     return d
 
 

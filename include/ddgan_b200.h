@@ -176,6 +176,8 @@ typedef struct {
   void* debug_prof;    /* optional int64[16] device buffer: per-role cycle counters of one CTA (tuning aid), or NULL */
   int batch_rows;      /* >0: batched GEMM (1x1 only): rows [b*batch_rows, (b+1)*batch_rows) use packed operand b
                           (wpack + b * ddg_conv_packed_bytes(...)); used for the attention GEMMs (layerspp.py:115-119) */
+  int zero_border;     /* 1 (PNHWC output only): `out` is a fresh, uninitialised buffer -- the kernel also clears its one-pixel frame
+                          (channels [0, Cout rounded up to the epilogue chunk)); 0: the frame is already zero and is left alone */
   void* out_planes;    /* optional (PNHWC output only): also write the result as pre-split bf16 planes [planes][N][out_C/8][H+2][W+2][8]
                           for consumers that read it without a prologue (see ddg_conv_src.planes) */
 } ddg_conv_desc;
@@ -250,7 +252,8 @@ typedef struct {
 int ddg_conv2d_wgrad(const ddg_wgrad_desc* desc, cudaStream_t stream);
 
 /* ---- PNHWC training helpers --------------------------------------------------------------------------------------
- * y = act(scale[n,c] * x + shift[n,c]) on the interior (border stays zero): AdaGN / GN apply + SiLU (layerspp.py:279,300) */
+ * y = act(scale[n,c] * x + shift[n,c]) on the interior: AdaGN / GN apply + SiLU (layerspp.py:279,300).  ddg_affine_act_fwd and
+ * ddg_gn_bwd_dx also clear the one-pixel frame of their output (it may be a fresh, uninitialised buffer). */
 int ddg_affine_act_fwd(const float* x, const float* scale, const float* shift, float* y, int N, int H, int W, int C, int act,
                        cudaStream_t stream);
 /* dx = dy * act'(u) * scale, sums[n][c] = {sum dy*act'(u)*x, sum dy*act'(u)} (float64, accumulated: zero it first) */
