@@ -144,6 +144,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_kernel(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();      // set-up above overlaps the tail of the previous kernel (PDL launch); q/k/v are read below
+  pdl_trigger();
 
   if (warp < kWorkWarps) {
     const int tid = threadIdx.x;
@@ -474,10 +476,10 @@ extern "C" int ddg_attention_fwd(const ddg_attn_desc* d, cudaStream_t stream) {
   static bool attr3 = false, attr1 = false;
   if (prec == 3) {
     if (!attr3) { cudaFuncSetAttribute(attn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr3 = true; }
-    attn_kernel<3><<<2 * d->N, kThreads, smem_bytes<3>(), stream>>>(p);
+    ddg::launch_pdl(attn_kernel<3>, dim3(2 * d->N), dim3(kThreads), smem_bytes<3>(), stream, p);
   } else {
     if (!attr1) { cudaFuncSetAttribute(attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr1 = true; }
-    attn_kernel<1><<<2 * d->N, kThreads, smem_bytes<1>(), stream>>>(p);
+    ddg::launch_pdl(attn_kernel<1>, dim3(2 * d->N), dim3(kThreads), smem_bytes<1>(), stream, p);
   }
   DDG_CHECK_LAUNCH();
   return DDG_OK;

@@ -16,6 +16,7 @@
   } while (0)
 
 void ddg_set_last_error(const char* msg);
+int ddg_pdl_enabled(void);   // api_common.cu: programmatic dependent launch switch (ddg_set_pdl / DDG_PDL)
 
 namespace ddg {
 
@@ -65,6 +66,27 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
   __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
   hi = *reinterpret_cast<uint32_t*>(&h);
   lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------------------
+// A kernel launched through launch_pdl() may start while the kernel in front of it on the stream is still draining: its CTAs are
+// scheduled, set up their shared memory / barriers / TMEM, and block in pdl_wait() until the predecessor has completed and its writes
+// are visible.  Rules every such kernel follows here: no global memory access before pdl_wait(), and pdl_trigger() only after
+// pdl_wait() -- so a dependent kernel can overlap its direct predecessor only, never anything older.  Without the launch attribute both
+// instructions are no-ops.  Works inside stream capture (the edge becomes a programmatic dependency of the CUDA graph).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ddg_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
 }  // namespace ddg

@@ -7,6 +7,8 @@ namespace ddg {
 
 // layers.py:475-486
 __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* __restrict__ out, int N, int dim, float log_max) {
+  pdl_wait();
+  pdl_trigger();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * dim) return;
@@ -28,6 +30,8 @@ constexpr int kLinKC = 1024;   // K chunk of the long-K variant
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                      const float* __restrict__ b, float* __restrict__ y, int N, int K, int J,
                                                      int ldx, int ldy, int act_in, int act_out, int pixel_norm, int cpw) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sx[];  // [kLinRows][K]
   const int n0 = blockIdx.y * kLinRows;
   const int rows = min(kLinRows, N - n0);
@@ -121,6 +125,8 @@ __global__ void q_sample_pairs_kernel(const float4* __restrict__ x0, const float
 __global__ void sample_posterior_kernel(const float4* __restrict__ x0, const float4* __restrict__ xt, const float4* __restrict__ nz,
                                         const int64_t* __restrict__ t, const float* __restrict__ c1, const float* __restrict__ c2,
                                         const float* __restrict__ logvar, float4* __restrict__ out, long per4, long total4) {
+  pdl_wait();
+  pdl_trigger();
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
     const int n = (int)(i / per4);
     const int tt = (int)t[n];
@@ -159,6 +165,8 @@ __global__ void sample_posterior_scalar(const float* x0, const float* xt, const 
 // NCHW (a ++ b along C) -> PNHWC interior, channels >= Ca+Cb zero.  One thread per (n, h, w); writes Cpad floats.
 __global__ void nchw_to_pnhwc_kernel(const float* __restrict__ a, int Ca, const float* __restrict__ b, int Cb, float* __restrict__ out,
                                      int N, int H, int W, int Cpad, float scale, float shift) {
+  pdl_wait();
+  pdl_trigger();
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   const long total = (long)N * H * W * (Cpad / 4);
   if (i >= total) return;
@@ -183,6 +191,8 @@ __global__ void nchw_to_pnhwc_kernel(const float* __restrict__ a, int Ca, const 
 // PNHWC / NHWC -> NCHW through a 32x32 smem transpose (coalesced on both sides)
 __global__ void pnhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ out, int N, int H, int W, int C, int Cpitch,
                                      int padded) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -208,6 +218,8 @@ __global__ void pnhwc_to_nchw_kernel(const float* __restrict__ x, float* __restr
 __global__ void gn_prepare_kernel(const double* __restrict__ sa, int Ca, const double* __restrict__ sb, int Cb,
                                   const float* __restrict__ gamma, const float* __restrict__ beta, int gb_stride, int per_sample,
                                   float* __restrict__ scale, float* __restrict__ shift, int HW, int G, float eps) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ double sred[];  // [2*C]
   const int n = blockIdx.x;
   const int C = Ca + Cb;
@@ -328,7 +340,7 @@ static inline int grid_for(long total, int threads, int cap = 148 * 32) {
 extern "C" int ddg_timestep_embedding(const int64_t* t, float* out, int N, int dim, float max_positions, cudaStream_t stream) {
   if (!t || !out || N <= 0 || dim < 4) { ddg_set_last_error("timestep_embedding: bad args"); return DDG_ERR_ARG; }
   const int total = N * dim;
-  timestep_embedding_kernel<<<(total + 255) / 256, 256, 0, stream>>>(t, out, N, dim, logf(max_positions));
+  launch_pdl(timestep_embedding_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, t, out, N, dim, logf(max_positions));
   DDG_CHECK_LAUNCH();
   return DDG_OK;
 }
@@ -350,7 +362,7 @@ extern "C" int ddg_linear(const float* x, const float* W, const float* b, float*
   if (!attr) { cudaFuncSetAttribute(linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
   const int cpw = J <= 2048 ? 1 : 4;
   dim3 grid((J + 8 * cpw - 1) / (8 * cpw), (N + kLinRows - 1) / kLinRows);
-  linear_kernel<<<grid, 256, smem, stream>>>(x, W, b, y, N, K, J, ldx, ldy, act_in, act_out, pixel_norm, cpw);
+  launch_pdl(linear_kernel, dim3(grid), dim3(256), smem, stream, x, W, b, y, N, K, J, ldx, ldy, act_in, act_out, pixel_norm, cpw);
   DDG_CHECK_LAUNCH();
   return DDG_OK;
 }
@@ -365,6 +377,8 @@ constexpr int kMlpRows = 2;
 constexpr int kMlpMaxDim = 1024;
 __global__ void __launch_bounds__(256) mlp_rows_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int N,
                                                        const ddg_mlp_desc d) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) float msm[];       // act[2][kMlpRows][kMlpMaxDim]
   float* act0 = msm;
   float* act1 = msm + kMlpRows * kMlpMaxDim;
@@ -461,7 +475,7 @@ extern "C" int ddg_mlp_rows(const float* x, int ldx, float* y, int ldy, int N, c
   const size_t smem = (size_t)(2 * ddg::kMlpRows * ddg::kMlpMaxDim) * sizeof(float);
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(ddg::mlp_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-  ddg::mlp_rows_kernel<<<(N + ddg::kMlpRows - 1) / ddg::kMlpRows, 256, smem, stream>>>(x, ldx, y, ldy, N, *desc);
+  ddg::launch_pdl(ddg::mlp_rows_kernel, dim3((N + ddg::kMlpRows - 1) / ddg::kMlpRows), dim3(256), smem, stream, x, ldx, y, ldy, N, *desc);
   DDG_CHECK_LAUNCH();
   return DDG_OK;
 }
@@ -487,8 +501,8 @@ extern "C" int ddg_sample_posterior(const float* x0, const float* x_t, const flo
   const long total = (long)N * per_sample;
   const bool vec = (per_sample % 4 == 0) && ((((uintptr_t)x0 | (uintptr_t)x_t | (uintptr_t)noise | (uintptr_t)out) & 15) == 0);
   if (vec)
-    sample_posterior_kernel<<<grid_for(total / 4, 256), 256, 0, stream>>>((const float4*)x0, (const float4*)x_t, (const float4*)noise, t, coef1, coef2,
-                                                                         logvar, (float4*)out, per_sample / 4, total / 4);
+    launch_pdl(sample_posterior_kernel, dim3(grid_for(total / 4, 256)), dim3(256), 0, stream, (const float4*)x0, (const float4*)x_t, (const float4*)noise, t,
+               coef1, coef2, logvar, (float4*)out, per_sample / 4, total / 4);
   else
     sample_posterior_scalar<<<grid_for(total, 256), 256, 0, stream>>>(x0, x_t, noise, t, coef1, coef2, logvar, out, per_sample, total);
   DDG_CHECK_LAUNCH();
@@ -499,7 +513,7 @@ extern "C" int ddg_nchw_to_pnhwc(const float* a, int Ca, const float* b, int Cb,
                                  float shift, cudaStream_t stream) {
   if (!a || !out || Cpad % 4 != 0 || Ca + Cb > Cpad) { ddg_set_last_error("nchw_to_pnhwc: bad args"); return DDG_ERR_ARG; }
   const long total = (long)N * H * W * (Cpad / 4);
-  nchw_to_pnhwc_kernel<<<(int)((total + 255) / 256), 256, 0, stream>>>(a, Ca, b, b ? Cb : 0, out, N, H, W, Cpad, scale, shift);
+  launch_pdl(nchw_to_pnhwc_kernel, dim3((int)((total + 255) / 256)), dim3(256), 0, stream, a, Ca, b, b ? Cb : 0, out, N, H, W, Cpad, scale, shift);
   DDG_CHECK_LAUNCH();
   return DDG_OK;
 }
@@ -507,7 +521,7 @@ extern "C" int ddg_nchw_to_pnhwc(const float* a, int Ca, const float* b, int Cb,
 extern "C" int ddg_pnhwc_to_nchw(const float* x, float* out, int N, int H, int W, int C, int Cpitch, int padded, cudaStream_t stream) {
   if (!x || !out) { ddg_set_last_error("pnhwc_to_nchw: bad args"); return DDG_ERR_ARG; }
   dim3 grid((H * W + 31) / 32, (C + 31) / 32, N), block(32, 8);
-  pnhwc_to_nchw_kernel<<<grid, block, 0, stream>>>(x, out, N, H, W, C, Cpitch, padded);
+  launch_pdl(pnhwc_to_nchw_kernel, grid, block, 0, stream, x, out, N, H, W, C, Cpitch, padded);
   DDG_CHECK_LAUNCH();
   return DDG_OK;
 }
@@ -517,8 +531,8 @@ extern "C" int ddg_gn_prepare(const double* stats_a, int Ca, const double* stats
                               cudaStream_t stream) {
   const int C = Ca + (stats_b ? Cb : 0);
   if (!stats_a || !scale || !shift || G <= 0 || C % G != 0) { ddg_set_last_error("gn_prepare: bad args"); return DDG_ERR_ARG; }
-  gn_prepare_kernel<<<N, 256, 2 * C * sizeof(double), stream>>>(stats_a, Ca, stats_b, stats_b ? Cb : 0, gamma, beta, gb_stride, per_sample,
-                                                                scale, shift, HW, G, eps);
+  launch_pdl(gn_prepare_kernel, dim3(N), dim3(256), 2 * C * sizeof(double), stream, stats_a, Ca, stats_b, stats_b ? Cb : 0, gamma, beta, gb_stride,
+             per_sample, scale, shift, HW, G, eps);
   DDG_CHECK_LAUNCH();
   return DDG_OK;
 }

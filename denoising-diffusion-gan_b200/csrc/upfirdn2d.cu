@@ -362,6 +362,8 @@ __device__ __forceinline__ void fma4(float4& a, const float4& v, float w) {
 __global__ void __launch_bounds__(256) fir_pnhwc_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                                         const float* __restrict__ shift, int act, float* __restrict__ out, int N, int H,
                                                         int W, int C, int mode, int out_pitch, float gain) {
+  pdl_wait();
+  pdl_trigger();
   const float t4[4] = {1.f, 3.f, 3.f, 1.f};
   const int C4 = C / 4;
   int OH, OW;
@@ -446,6 +448,8 @@ template <int MODE>
 __global__ void __launch_bounds__(256) fir_pnhwc_tiled_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                                               const float* __restrict__ shift, int act, float* __restrict__ out, int H,
                                                               int W, int C, int out_pitch, float gain, int tiles_x) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int OT = MODE == 1 ? 16 : 8;             // output tile edge
   constexpr int IT = MODE == 1 ? 10 : 18;            // input window edge
   constexpr int CB = 32, CB4 = CB / 4;
@@ -570,15 +574,15 @@ extern "C" int ddg_fir_pnhwc(const float* x, const float* scale, const float* sh
     const int OT = mode == 1 ? 16 : 8;
     const int tiles_x = (OW + OT - 1) / OT, tiles_y = (OH + OT - 1) / OT;
     dim3 grid(tiles_x * tiles_y, C / 32, N);
-    if (mode == 1) fir_pnhwc_tiled_kernel<1><<<grid, 256, 0, stream>>>(x, scale, shift, act, out, H, W, C, out_pitch, gain, tiles_x);
-    else fir_pnhwc_tiled_kernel<2><<<grid, 256, 0, stream>>>(x, scale, shift, act, out, H, W, C, out_pitch, gain, tiles_x);
+    if (mode == 1) launch_pdl(fir_pnhwc_tiled_kernel<1>, dim3(grid), dim3(256), 0, stream, x, scale, shift, act, out, H, W, C, out_pitch, gain, tiles_x);
+    else launch_pdl(fir_pnhwc_tiled_kernel<2>, dim3(grid), dim3(256), 0, stream, x, scale, shift, act, out, H, W, C, out_pitch, gain, tiles_x);
     DDG_CHECK_LAUNCH();
     return DDG_OK;
   }
   const long total = (long)N * OH * OW * (C / 4);
   long blocks = (total + 255) / 256;
   if (blocks > 148L * 32) blocks = 148L * 32;
-  fir_pnhwc_kernel<<<(int)blocks, 256, 0, stream>>>(x, scale, shift, act, out, N, H, W, C, mode, out_pitch, gain);
+  launch_pdl(fir_pnhwc_kernel, dim3((int)blocks), dim3(256), 0, stream, x, scale, shift, act, out, N, H, W, C, mode, out_pitch, gain);
   DDG_CHECK_LAUNCH();
   return DDG_OK;
 }

@@ -86,6 +86,7 @@ _SIGNATURES = {
     'ddg_conv_last_launch_info': ([_P, _P, _P, _P], _I),
     'ddg_conv_last_launch_tma': ([], _I),
     'ddg_zero_border': ([_P] + [_I] * 4 + [_P], _I),
+    'ddg_set_pdl': ([_I], _I),
     'ddg_softmax_rows': ([_P, _P, _L, _I, _I, _I, _P], _I),
     'ddg_softmax_rows_bwd': ([_P, _P, _P, _L, _I, _I, _F, _P], _I),
     'ddg_conv_tile_n': ([_I, _L], _I),

@@ -111,12 +111,10 @@ class _EngineBase:
         """Pre-split bf16 planes of an activation for consumers that read it raw (1x1 skip convs): written by the producing conv's
         epilogue when there is one (no extra pass), else by a split kernel placed here in the plan.  None when the geometry is
         not the 2-D tiling the TMA path covers (H % 16, W % 8)."""
-        # Measured on B200 (CIFAR NCSN++, batch 64, whole sampling step): BF16 mode 4529 -> 4612 images/s with the planes (the TMA
-        # moves half the bytes of the fp32 path and no conversion is left); BF16x3 mode 3831 -> 3760 (hi + lo planes are as many
-        # bytes as the fp32 rows, so only the conversion is saved, and the extra epilogue stores / split passes cost more than
-        # that).  Hence: on by default in BF16 mode only; DDG_ENGINE_PLANES=0/1 overrides.
-        want = os.environ.get('DDG_ENGINE_PLANES')
-        on = (self.prec == 1) if want is None else (want == '1')
+        # Measured on B200 (CIFAR NCSN++, batch 64, whole sampling step) with the 4-D tensor map (160-byte box rows): BF16 mode
+        # 4529 -> 4658 images/s, BF16x3 mode 3802 -> 3850.  (The first tensor map had a separate 8-channel inner dimension -- 16-byte
+        # rows -- and lost to the fp32 producer path in BF16x3 mode.)  On by default; DDG_ENGINE_PLANES=0 turns it off.
+        on = os.environ.get('DDG_ENGINE_PLANES', '1') == '1'
         if not on or act.H % 16 != 0 or act.W % 8 != 0:
             return None
         if act.planes is None:

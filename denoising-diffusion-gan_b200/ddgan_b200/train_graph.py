@@ -100,12 +100,6 @@ def freeze_packs(mod):
 
 _CUR_PACKS = [None]
 
-# The conv epilogue can clear the frame of a fresh output buffer itself (ddg_conv_desc.zero_border) instead of a separate
-# ddg_zero_border launch.  Measured on the CIFAR train step: 270 launches (0.9 ms) saved, but the edge stores in the epilogue cost
-# the tensor-core kernels 1.3 ms -> off by default (the elementwise kernels ddg_affine_act_fwd / ddg_gn_bwd_dx do clear their own
-# frames: +0.13 ms of kernel time for 122 launches = 0.34 ms saved).
-import os as _os
-_CONV_ZERO_BORDER = _os.environ.get('DDG_CONV_ZERO_BORDER') == '1'
 
 # module -> callable fired in the backward pass when the up path + head have been differentiated (see generator_forward).  Kept
 # outside the module so that copy.deepcopy / pickling of the network never drags a Trainer along.
@@ -151,13 +145,11 @@ def _conv_forward(x, w, bias, addvec, sp, res=None, w_ref=None):
         out = torch.zeros(sp.n, sp.cout, sp.hout, sp.wout, device=x.device)
         mode, out_c = ops.OUT_NCHW, 0
     else:
-        zb = _CONV_ZERO_BORDER and sp.cout == sp.cpad_out
-        out = ops.alloc_pnhwc(sp.n, sp.hout, sp.wout, sp.cpad_out, x.device, full=(sp.cout != sp.cpad_out), border=not zb)
+        out = ops.alloc_pnhwc(sp.n, sp.hout, sp.wout, sp.cpad_out, x.device, full=(sp.cout != sp.cpad_out))
         mode, out_c = ops.OUT_PNHWC, sp.cpad_out
     ops.conv2d_fused(cw, [ops.conv_src(x, sp.cpad_in, sp.taps)], sp.n, sp.hout, sp.wout, out, out_mode=mode, out_c=out_c,
                      hp=sp.hp, wp=sp.wp, bias=bias, addvec=(addvec[0] if addvec is not None else None),
-                     addvec_stride=(addvec[1] if addvec is not None else 0), res=res, out_scale=sp.out_scale,
-                     zero_border=int(mode == ops.OUT_PNHWC and sp.cout == sp.cpad_out and _CONV_ZERO_BORDER))
+                     addvec_stride=(addvec[1] if addvec is not None else 0), res=res, out_scale=sp.out_scale)
     return out
 
 
@@ -260,10 +252,9 @@ class DgradFn(Function):
         dye = _embed(dy, sp.hp, sp.wp).contiguous()
         cy = dye.shape[-1]
         cw = _packed(w, w_ref, 'dgrad', sp, dy.device, cy=cy)
-        dx = ops.alloc_pnhwc(sp.n, sp.hp - 2, sp.wp - 2, sp.cpad_in, dy.device, full=False, border=not _CONV_ZERO_BORDER)
+        dx = ops.alloc_pnhwc(sp.n, sp.hp - 2, sp.wp - 2, sp.cpad_in, dy.device, full=False)
         taps = [(-dr, -ds) for dr, ds in sp.taps]
-        ops.conv2d_fused(cw, [ops.conv_src(dye, cy, taps)], sp.n, sp.hp - 2, sp.wp - 2, dx, out_scale=sp.out_scale,
-                         zero_border=int(_CONV_ZERO_BORDER))
+        ops.conv2d_fused(cw, [ops.conv_src(dye, cy, taps)], sp.n, sp.hp - 2, sp.wp - 2, dx, out_scale=sp.out_scale)
         if sp.cin < sp.cpad_in:
             dx[..., sp.cin:] = 0
         return dx

@@ -120,6 +120,11 @@ int ddg_minibatch_stddev(const float* x, float* out, int N, int H, int W, int C,
 int ddg_spatial_sum(const float* x, float* out, int N, int H, int W, int C, int act, cudaStream_t stream);
 /* zero the one-pixel frame of a PNHWC buffer [N][H+2][W+2][C] (C % 4 == 0): kernels write interiors only, so a fresh buffer needs
  * just its border cleared to serve as the zero padding of the next 3x3 conv (ncsnpp convs use padding=1, layerspp.py:33) */
+/* Programmatic dependent launch (CUDA PDL) for the kernels of the generator / discriminator forward path: a kernel's CTAs are
+ * scheduled and set up while its predecessor on the stream drains, and block (griddepcontrol.wait) before their first global access.
+ * Off by default (environment DDG_PDL=1 turns it on: it measured neutral on the captured loops); returns the previous setting.  No reference counterpart: the reference's
+ * launches are PyTorch's. */
+int ddg_set_pdl(int on);
 int ddg_zero_border(float* buf, int N, int H, int W, int C, cudaStream_t stream);
 /* row softmax of the attention logits (layerspp.py:116-118): p[r][0:T] = softmax(s[r][0:T]), p[r][T:ldp] = 0 */
 int ddg_softmax_rows(const float* s, float* p, long rows, int T, int lds, int ldp, cudaStream_t stream);
@@ -176,8 +181,8 @@ typedef struct {
   void* debug_prof;    /* optional int64[16] device buffer: per-role cycle counters of one CTA (tuning aid), or NULL */
   int batch_rows;      /* >0: batched GEMM (1x1 only): rows [b*batch_rows, (b+1)*batch_rows) use packed operand b
                           (wpack + b * ddg_conv_packed_bytes(...)); used for the attention GEMMs (layerspp.py:115-119) */
-  int zero_border;     /* 1 (PNHWC output only): `out` is a fresh, uninitialised buffer -- the kernel also clears its one-pixel frame
-                          (channels [0, Cout rounded up to the epilogue chunk)); 0: the frame is already zero and is left alone */
+  int zero_border;     /* 1 (PNHWC output only): `out` is a fresh, uninitialised buffer -- its one-pixel frame is cleared first
+                          (ddg_zero_border on the same stream); 0: the frame is already zero and is left alone */
   void* out_planes;    /* optional (PNHWC output only): also write the result as pre-split bf16 planes [planes][N][out_C/8][H+2][W+2][8]
                           for consumers that read it without a prologue (see ddg_conv_src.planes) */
 } ddg_conv_desc;

@@ -30,6 +30,15 @@ def run(n, cin, cout, h, k, msub=0, affine=True, prec=3, nt256=1, stats=True):
     pv = prof.cpu().tolist()
     print(f'conv {cin}->{cout} {k}x{k} @{h}px n={n} msub={msub} prec={prec} nt256={nt256} stats={stats}: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s')
     print('   ' + '  '.join(f'{a}={b}' for a, b in zip(names, pv)))
-run(64, 128, 128, 32, 3)
-run(64, 256, 256, 32, 3)
-run(64, 256, 768, 16, 1)
+if __name__ == '__main__':
+    which = sys.argv[1] if len(sys.argv) > 1 else 'big'
+    if which == 'big':
+        run(64, 128, 128, 32, 3)
+        run(64, 256, 256, 32, 3)
+        run(64, 256, 768, 16, 1)
+    else:   # the small levels (4x4, 8x8): N = 64 / 128 one-tile CTAs
+        run(64, 256, 256, 4, 3)
+        run(64, 256, 256, 8, 3)
+        run(64, 256, 256, 8, 3, nt256=1 | 2)
+        run(64, 256, 256, 4, 3, affine=False, stats=False)
+        run(64, 256, 256, 16, 3)
