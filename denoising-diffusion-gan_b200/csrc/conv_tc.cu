@@ -75,6 +75,12 @@ __device__ __forceinline__ void tma_tensor_4d_g2s(uint32_t dst, const void* tmap
       : "memory");
 }
 
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* ptr) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -216,6 +222,12 @@ struct ConvDev {
   int tma_pitch;               // chunk pitch of a TMA-written A plane: window rows * 16 bytes, dense (producer planes are padded)
   void* out_planes;            // optional pre-split copy of the PNHWC output (see ddg_conv_desc.out_planes)
   long out_plane_bytes;
+  // split-K (one-tile CTAs on the small spatial levels): ksplit CTAs share an output tile, CTA rank r runs K blocks
+  // [kb_split[r], kb_split[r+1]); ranks 0..ksplit-2 park their fp32 partial accumulators in ws_part, the last rank adds them in its epilogue
+  int ksplit;
+  int kb_split[5];
+  float* ws_part;              // [tile][ksplit-1][128*MSUB][NT] fp32
+  unsigned* ws_flag;           // [tile] arrival counters (zero between launches)
   alignas(64) CUtensorMap tmap[DDG_CONV_MAX_SRC][2];   // hi / lo plane of every TMA-fed source
 };
 
@@ -311,7 +323,7 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
   auto set_tile = [&](int tile) {
     int mx;
     if (PERSIST) { ntile = tile / p.tiles_m; mx = tile - ntile * p.tiles_m; }
-    else { mx = blockIdx.x; ntile = blockIdx.y; }
+    else { mx = blockIdx.x / p.ksplit; ntile = blockIdx.y; }
     m0 = (p.batch_rows > 0 ? blockIdx.z * p.batch_rows : 0) + mx * MT;
     m_end = p.batch_rows > 0 ? (blockIdx.z + 1) * p.batch_rows : p.Mtotal;
     if (p.tile2d) {
@@ -344,6 +356,11 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
   // number of K blocks
   int nkb_total = 0;
   for (int s = 0; s < p.nsrc; ++s) nkb_total += p.src[s].C / KB;
+  // split-K: this CTA's share of the K blocks (the whole range unless ksplit > 1; never in the persistent variant)
+  const int krank = PERSIST ? 0 : (int)(blockIdx.x % p.ksplit);
+  const int kb_lo = (!PERSIST && p.ksplit > 1) ? p.kb_split[krank] : 0;
+  const int kb_hi = (!PERSIST && p.ksplit > 1) ? p.kb_split[krank + 1] : nkb_total;
+  const int tile_id = PERSIST ? 0 : (int)(blockIdx.y * (gridDim.x / p.ksplit) + blockIdx.x / p.ksplit);
 
   // =================================== epilogue (one tile) ===================================
   // quad: TMEM lane quadrant of the calling warp; the warp handles column chunks half0, half0 + hstep, ...
@@ -393,20 +410,31 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
     if (own_stage && half0 < NU) load_rows(half0 / NCHUNK);   // (before the wait: overlaps the end of the mainloop)
     if (wait_acc) mbar_wait(accFull(ab), PERSIST ? ((it >> 1) & 1) : 0);
     tc_fence_after();
+    // split-K: ranks 0 .. ksplit-2 only park their partial accumulators; the last rank (highest block index of the tile, so that
+    // in-order CTA dispatch has put its writers on the machine before it) waits for them and adds them before the usual epilogue.
+    const bool sk_writer = !PERSIST && p.ksplit > 1 && krank < p.ksplit - 1;
+    const bool sk_reduce = !PERSIST && p.ksplit > 1 && krank == p.ksplit - 1;
+    if (sk_reduce) {
+      if (lane == 0) {
+        const unsigned want = (unsigned)(p.ksplit - 1) * kProdWarps;     // one arrival per epilogue warp of every writer CTA
+        while (ld_acquire_gpu(p.ws_flag + tile_id) < want) { }
+      }
+      __syncwarp();
+    }
 #pragma unroll 1
     for (int u = half0; u < NU; u += hstep) {
       const int sub = u / NCHUNK, ck = u - sub * NCHUNK;
       const int col0 = ntile * NT + ck * CW;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * ACC_COLS + sub * NT + ck * CW);
       if (col0 >= p.Cout) continue;
-      if (sub != sub_cur) load_rows(sub);
+      if (sub != sub_cur && !sk_writer) load_rows(sub);
       const bool fast = (CW == 32) && (p.out_mode != 2) && (col0 + CW <= p.Cout);
       float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), av0 = b4, av1 = b4;
       float4 rs[4];
       {
         float v[CW];
         if (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
-        if (CW == 32 && fast) {
+        if (CW == 32 && fast && !sk_writer) {
           // operands that do not depend on the accumulators are put in flight before the TMEM wait
           if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c4));
           if (p.addvec) {
@@ -421,6 +449,24 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
           }
         }
         tmem_ld_wait();
+        if (sk_writer || sk_reduce) {
+          const size_t prow = (size_t)(sub * 128 + quad * 32 + lane) * NT + ck * CW;   // thread = accumulator row: 128 contiguous bytes
+          if (sk_writer) {
+            float4* dst = reinterpret_cast<float4*>(p.ws_part + ((size_t)(tile_id * (p.ksplit - 1) + krank) * MT) * NT + prow);
+#pragma unroll
+            for (int j = 0; j < CW / 4; ++j) __stcg(dst + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+            continue;
+          }
+#pragma unroll 1
+          for (int r = 0; r < p.ksplit - 1; ++r) {
+            const float4* src = reinterpret_cast<const float4*>(p.ws_part + ((size_t)(tile_id * (p.ksplit - 1) + r) * MT) * NT + prow);
+#pragma unroll
+            for (int j = 0; j < CW / 4; ++j) {
+              const float4 t = __ldcg(src + j);
+              v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+            }
+          }
+        }
         __syncwarp();                                  // the previous unit has been read out of the staging tile
         float4* s4 = reinterpret_cast<float4*>(stg + lane * 36);   // pitch 36 floats: the 8 lanes of a store phase hit 32 distinct banks
 #pragma unroll
@@ -534,6 +580,11 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
           }
         }
       }
+    }
+    if (sk_writer) {                                   // partials of this warp are out: publish them (fence, then one arrival per warp)
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicAdd(p.ws_flag + tile_id, 1u);
     }
     // accumulator set drained: hand it back to the MMA issuer
     tc_fence_before();
@@ -652,22 +703,23 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
       if (it == 0) t_prod0 = DDG_CLK();
     float cur[IMAX][8], nxt[IMAX][8];
     int off_c[IMAX], nn_c[IMAX], off_n[IMAX], nn_n[IMAX];
-    int s_cur = 0, kb_cur = 0;
-    if (!p.src[0].tma) {
+    int s_cur = 0, kb_cur = kb_lo;                     // (source, K block inside it) of the first K block of this CTA
+    while (kb_cur >= p.src[s_cur].C / KB) { kb_cur -= p.src[s_cur].C / KB; ++s_cur; }
+    if (!p.src[s_cur].tma) {
       int lo_, hi_;
-      src_rows(p.src[0], lo_, hi_);
+      src_rows(p.src[s_cur], lo_, hi_);
 #pragma unroll
       for (int k = 0; k < IMAX; ++k) {
-        row_info(p.src[0], lo_ + e0 + k * ESTEP, hi_, off_c[k], nn_c[k]);
+        row_info(p.src[s_cur], lo_ + e0 + k * ESTEP, hi_, off_c[k], nn_c[k]);
         if (off_c[k] >= 0) {
-          const float4* q = reinterpret_cast<const float4*>(p.src[0].x + off_c[k] + c * 8);
+          const float4* q = reinterpret_cast<const float4*>(p.src[s_cur].x + off_c[k] + kb_cur * KB + c * 8);
           const float4 a = __ldg(q), b = __ldg(q + 1);
           cur[k][0] = a.x; cur[k][1] = a.y; cur[k][2] = a.z; cur[k][3] = a.w;
           cur[k][4] = b.x; cur[k][5] = b.y; cur[k][6] = b.z; cur[k][7] = b.w;
         }
       }
     }
-    for (int kb_idx = 0; kb_idx < nkb_total; ++kb_idx) {
+    for (int kb_idx = kb_lo; kb_idx < kb_hi; ++kb_idx) {
       const SrcDev& S = p.src[s_cur];
       // ---- scale / shift of this K-block's first live row, issued ahead of the prefetch so that its latency overlaps the
       //      prefetch issue and the wait for a free A stage (it used to be a dependent load in front of the first FFMA) ----
@@ -690,7 +742,7 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
       // ---- prefetch the next K-block ----
       int s_nxt = s_cur, kb_nxt = kb_cur + 1;
       if (kb_nxt >= S.C / KB) { s_nxt = s_cur + 1; kb_nxt = 0; }
-      const bool has_next = kb_idx + 1 < nkb_total;
+      const bool has_next = kb_idx + 1 < kb_hi;
       if (has_next && !p.src[s_nxt].tma) {
         const SrcDev& Sn = p.src[s_nxt];
         if (s_nxt != s_cur) {
@@ -801,10 +853,11 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
         set_tile(tile);
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)ntile * p.total_stages * Cfg::B_STAGE +
                               (p.batch_rows > 0 ? (size_t)blockIdx.z * p.w_batch_stride : 0);
-        int i = 0;
+        int i = 0, kbi = 0;
         for (int s = 0; s < p.nsrc; ++s) {
           const SrcDev& S = p.src[s];
-          for (int kb = 0; kb < S.C / KB; ++kb) {
+          for (int kb = 0; kb < S.C / KB; ++kb, ++kbi) {
+            if (kbi < kb_lo || kbi >= kb_hi) { i += S.ntaps; continue; }     // another CTA's share of K (split-K)
             mbar_wait(emptyA(stA_l), phA_l ^ 1);
             if (S.tma) {
               // halo window (16*MSUB+2 rows x 10 columns) x 4 chunks of 8 channels, from the padded planes [n][chunk][y][x][8]
@@ -862,6 +915,10 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
       int s_m = 0, kb_m = 0;
       for (int kb_idx = 0; kb_idx < nkb_total; ++kb_idx) {
         const SrcDev& S = p.src[s_m];
+        if (kb_idx < kb_lo || kb_idx >= kb_hi) {        // another CTA's share of K (split-K)
+          if (++kb_m >= S.C / KB) { kb_m = 0; ++s_m; }
+          continue;
+        }
         const int stA = stA_m;
         { const long long tw = DDG_CLK(); mbar_wait(fullA(stA), phA_m); w_fullA += DDG_CLK() - tw; }
         if (++stA_m == NSA) { stA_m = 0; phA_m ^= 1u; }
@@ -940,6 +997,7 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
   }
 
   __syncthreads();
+  if (!PERSIST && p.ksplit > 1 && krank == p.ksplit - 1 && threadIdx.x == 0) p.ws_flag[tile_id] = 0u;   // ready for the next launch
   if (warp == kProdWarps + 1) {
     tc_fence_after();
     tmem_dealloc<TM_COLS>(tmem_base);
@@ -1001,7 +1059,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
 struct Variant { int msub, nt, kb; };
 
 static int g_small_nt64 = 1;
-static thread_local int g_last_info[5] = {0, 0, 0, 0, 0};   // msub, nt, persistent, CTAs, TMA-fed K segments of the last launch
+static thread_local int g_last_info[6] = {0, 0, 0, 0, 0, 1};   // msub, nt, persistent, CTAs, TMA-fed K segments, split-K factor of the last launch
+static int g_splitk = getenv("DDG_CONV_NO_SPLITK") ? 0 : 1;
 static int g_persist = getenv("DDG_CONV_NO_PERSIST") ? 0 : 1;   // persistent variant (epilogue overlapped with the next tile's mainloop) when tiles > SMs
 static int num_sms() {
   static int n = 0;
@@ -1056,6 +1115,10 @@ static int launch_conv(ConvDev& d, int n_tiles, cudaStream_t stream) {
     const long total = (long)grid.x * n_tiles;
     grid = dim3((unsigned)(total < num_sms() ? total : num_sms()));
     g_last_info[3] = (int)grid.x;
+    d.ksplit = 1;
+  } else if (d.ksplit > 1) {
+    grid.x *= d.ksplit;                   // the ksplit CTAs of a tile are neighbours in block order
+    g_last_info[3] *= d.ksplit;
   }
   launch_pdl(kern, grid, dim3(PERSIST ? kThreadsPersist : kThreads), smem, stream, d);
   DDG_CHECK_LAUNCH();
@@ -1135,6 +1198,7 @@ extern "C" int ddg_split_planes(const float* x, void* planes, int N, int H, int 
 
 extern "C" int ddg_conv_tile_n(int cout, long m_rows) { return pick_nt(cout, m_rows); }
 extern "C" int ddg_conv_last_launch_tma(void) { return g_last_info[4]; }
+extern "C" int ddg_conv_last_launch_ksplit(void) { return g_last_info[5]; }
 extern "C" int ddg_conv_last_launch_info(int* msub, int* nt, int* persistent, int* grid_ctas) {
   if (msub) *msub = g_last_info[0];
   if (nt) *nt = g_last_info[1];
@@ -1305,6 +1369,37 @@ extern "C" int ddg_conv2d_fwd(const ddg_conv_desc* c, cudaStream_t stream) {
   if ((long)c->N * (c->Hout + 2) * (c->Wout + 2) >= (1L << 31)) { ddg_set_last_error("conv2d_fwd: more than 2^31 output pixels"); return DDG_ERR_UNSUPPORTED; }
   d.out_planes = (c->out_mode == 0) ? c->out_planes : nullptr;
   d.out_plane_bytes = ddg_planes_bytes(d.N, d.Hout, d.Wout, d.out_C);
+
+  // split-K for grids that leave most of the machine idle (4x4 / 8x8 levels: a few dozen one-tile CTAs, each a serial chain of
+  // K/16 * 3 MMAs): ksplit CTAs per tile, all resident at once (tiles * ksplit <= SMs), reduction through the caller's workspace.
+  d.ksplit = 1;
+  if (g_splitk && !persist && c->splitk_ws != nullptr && c->batch_rows == 0 && nt >= 64 && c->debug_prof == nullptr) {
+    const long tiles = (tile2d ? (long)d.N * (d.Hout / (16 * msub)) * (d.Wout / 8) : ((long)d.Mtotal + MT - 1) / MT) * n_tiles;
+    int nkb = 0;
+    for (int s = 0; s < c->nsrc; ++s) nkb += c->src[s].C / KB;
+    for (int cand = 4; cand >= 2 && d.ksplit == 1; cand -= 2) {
+      if (tiles * cand > num_sms() || nkb < 2 * cand) continue;
+      const long need = 4096 + tiles * (cand - 1) * (long)MT * nt * 4;
+      if (tiles * 4 > 4096 || need > c->splitk_ws_bytes) continue;
+      // balance by B stages (a K block of a 3x3 segment carries nine of them, one of a 1x1 segment)
+      int split[5] = {0, 0, 0, 0, 0}, r = 1, kbi = 0;
+      long acc_st = 0;
+      for (int s = 0; s < c->nsrc && r < cand; ++s)
+        for (int kb = 0; kb < c->src[s].C / KB && r < cand; ++kb, ++kbi) {
+          acc_st += c->src[s].ntaps;
+          if (acc_st * cand >= (long)total_stages * r) split[r++] = kbi + 1;
+        }
+      split[cand] = nkb;
+      bool ok = (r == cand);
+      for (int q = 0; q < cand && ok; ++q) ok = split[q + 1] > split[q];
+      if (!ok) continue;
+      d.ksplit = cand;
+      for (int q = 0; q <= cand; ++q) d.kb_split[q] = split[q];
+      d.ws_flag = reinterpret_cast<unsigned*>(c->splitk_ws);
+      d.ws_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(c->splitk_ws) + 4096);
+    }
+  }
+  g_last_info[5] = d.ksplit;
 
   // tuning builds with cycle counters (tools/conv_prof.py): the three shapes that dominate a generator forward
   if (d.prof != nullptr && prec == 3) {

@@ -28,7 +28,8 @@ class ConvDesc(C.Structure):
                 ('bias', C.c_void_p), ('addvec', C.c_void_p), ('addvec_stride', C.c_int), ('res', C.c_void_p),
                 ('out_scale', C.c_float), ('out_act', C.c_int), ('out', C.c_void_p), ('out_mode', C.c_int),
                 ('out_C', C.c_int), ('stats', C.c_void_p), ('precision', C.c_int), ('msub', C.c_int),
-                ('force_linear', C.c_int), ('debug_prof', C.c_void_p), ('batch_rows', C.c_int), ('zero_border', C.c_int), ('out_planes', C.c_void_p)]
+                ('force_linear', C.c_int), ('debug_prof', C.c_void_p), ('batch_rows', C.c_int), ('zero_border', C.c_int), ('out_planes', C.c_void_p),
+                ('splitk_ws', C.c_void_p), ('splitk_ws_bytes', C.c_long)]
 
 
 class WgradDesc(C.Structure):
@@ -85,6 +86,7 @@ _SIGNATURES = {
     'ddg_spatial_sum': ([_P, _P] + [_I] * 5 + [_P], _I),
     'ddg_conv_last_launch_info': ([_P, _P, _P, _P], _I),
     'ddg_conv_last_launch_tma': ([], _I),
+    'ddg_conv_last_launch_ksplit': ([], _I),
     'ddg_zero_border': ([_P] + [_I] * 4 + [_P], _I),
     'ddg_set_pdl': ([_I], _I),
     'ddg_softmax_rows': ([_P, _P, _L, _I, _I, _I, _P], _I),

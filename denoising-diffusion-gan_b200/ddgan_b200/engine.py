@@ -61,6 +61,7 @@ class _EngineBase:
         else:
             self.P = {k: torch.zeros(v, device=self.dev) for k, v in shapes.items()}  # fixed-address parameter copies
         self._pack_plan = None
+        self._splitk_ws = ops.alloc_splitk_ws(self.dev)   # split-K workspace of the 4x4 / 8x8 level convs (one stream: shared by all)
         self.steps = []      # zero-arg callables, executed in order on the current stream
         self.step_names = []
         self.binders = []    # zero-arg callables that (re)pack derived weights from self.P
@@ -95,6 +96,7 @@ class _EngineBase:
         window = any(len(s_['taps']) > 1 for s_ in srcs)
         m_rows = n * kw.get('hp', hout + 2) * kw.get('wp', wout + 2) if window else n * hout * wout
         cw = ops.ConvWeights(cout, [(s['C'], len(s['taps'])) for s in srcs], self.dev, precision=self.prec, m_rows=m_rows)
+        kw.setdefault('splitk_ws', self._splitk_ws)
         desc = ops.build_conv_desc(cw, srcs, n, hout, wout, out, **kw)
         self._last_desc = desc
         self._keep.append((cw, desc, srcs, kw, out))

@@ -592,6 +592,12 @@ def alloc_planes(n, h, w, c, precision, device):
     return torch.zeros(npl * lib().ddg_planes_bytes(n, h, w, c), dtype=torch.uint8, device=device)
 
 
+def alloc_splitk_ws(device, nbytes=8 << 20):
+    """Workspace for the split-K convolutions of the small spatial levels (ddg_conv_desc.splitk_ws): arrival counters + fp32 partial
+    tiles.  One buffer serves every convolution launched on one stream."""
+    return torch.zeros(nbytes, dtype=torch.uint8, device=device)
+
+
 def split_planes(x, planes, precision):
     n, hp, wp, c = x.shape
     check(lib().ddg_split_planes(ptr(x), ptr(planes), n, hp - 2, wp - 2, c, 2 if precision == 3 else 1, stream()), 'split_planes')
@@ -604,7 +610,7 @@ def _addr(v):
 
 def build_conv_desc(weights: ConvWeights, srcs, n, hout, wout, out, out_mode=OUT_PNHWC, hp=None, wp=None, bias=None, addvec=None,
                     addvec_stride=0, res=None, out_scale=1.0, out_act=ACT_NONE, out_c=0, stats=None, msub=0, batch_rows=0, prof=None, force_linear=0,
-                    out_planes=None, zero_border=0) -> ConvDesc:
+                    out_planes=None, zero_border=0, splitk_ws=None) -> ConvDesc:
     d = ConvDesc()
     d.nsrc = len(srcs)
     for i, s in enumerate(srcs):
@@ -634,6 +640,9 @@ def build_conv_desc(weights: ConvWeights, srcs, n, hout, wout, out, out_mode=OUT
     d.force_linear = force_linear
     d.out_planes = _addr(out_planes)
     d.zero_border = int(zero_border)
+    if splitk_ws is not None:          # uint8 tensor, zero-initialised once (alloc_splitk_ws); shared by the launches of one stream
+        d.splitk_ws = splitk_ws.data_ptr()
+        d.splitk_ws_bytes = splitk_ws.numel()
     return d
 
 

@@ -100,6 +100,19 @@ def freeze_packs(mod):
 
 _CUR_PACKS = [None]
 
+# split-K workspace of the small-level convolutions (ddg_conv_desc.splitk_ws): every conv of the training graphs is launched on the
+# stream the step runs on (eager: autograd replays the backward on the forward's stream; captured: the capture stream), so one buffer
+# per (device, stream) is enough
+_SPLITK_WS = {}
+
+
+def _splitk_ws(dev):
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _SPLITK_WS.get(key)
+    if ws is None:
+        ws = _SPLITK_WS[key] = ops.alloc_splitk_ws(dev)
+    return ws
+
 
 # module -> callable fired in the backward pass when the up path + head have been differentiated (see generator_forward).  Kept
 # outside the module so that copy.deepcopy / pickling of the network never drags a Trainer along.
@@ -149,7 +162,7 @@ def _conv_forward(x, w, bias, addvec, sp, res=None, w_ref=None):
         mode, out_c = ops.OUT_PNHWC, sp.cpad_out
     ops.conv2d_fused(cw, [ops.conv_src(x, sp.cpad_in, sp.taps)], sp.n, sp.hout, sp.wout, out, out_mode=mode, out_c=out_c,
                      hp=sp.hp, wp=sp.wp, bias=bias, addvec=(addvec[0] if addvec is not None else None),
-                     addvec_stride=(addvec[1] if addvec is not None else 0), res=res, out_scale=sp.out_scale)
+                     addvec_stride=(addvec[1] if addvec is not None else 0), res=res, out_scale=sp.out_scale, splitk_ws=_splitk_ws(x.device))
     return out
 
 
@@ -254,7 +267,8 @@ class DgradFn(Function):
         cw = _packed(w, w_ref, 'dgrad', sp, dy.device, cy=cy)
         dx = ops.alloc_pnhwc(sp.n, sp.hp - 2, sp.wp - 2, sp.cpad_in, dy.device, full=False)
         taps = [(-dr, -ds) for dr, ds in sp.taps]
-        ops.conv2d_fused(cw, [ops.conv_src(dye, cy, taps)], sp.n, sp.hp - 2, sp.wp - 2, dx, out_scale=sp.out_scale)
+        ops.conv2d_fused(cw, [ops.conv_src(dye, cy, taps)], sp.n, sp.hp - 2, sp.wp - 2, dx, out_scale=sp.out_scale,
+                         splitk_ws=_splitk_ws(dy.device))
         if sp.cin < sp.cpad_in:
             dx[..., sp.cin:] = 0
         return dx

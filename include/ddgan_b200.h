@@ -185,6 +185,10 @@ typedef struct {
                           (ddg_zero_border on the same stream); 0: the frame is already zero and is left alone */
   void* out_planes;    /* optional (PNHWC output only): also write the result as pre-split bf16 planes [planes][N][out_C/8][H+2][W+2][8]
                           for consumers that read it without a prologue (see ddg_conv_src.planes) */
+  void* splitk_ws;     /* optional split-K workspace (device memory, zero-initialised once by the caller; any number of launches on ONE
+                          stream may share it).  With it, layers whose grid would leave most SMs idle (4x4 / 8x8 levels) run 2 or 4
+                          CTAs per output tile, each over a share of K; the partial sums meet in this buffer.  NULL: never split. */
+  long splitk_ws_bytes;/* size of splitk_ws; layers that would need more fall back to one CTA per tile */
 } ddg_conv_desc;
 
 /* output-channel tile width the conv kernel will use for a problem with m_rows GEMM rows (pack and launch must agree) */
@@ -218,6 +222,7 @@ long ddg_planes_bytes(int N, int H, int W, int C);
 int ddg_conv_last_launch_info(int* msub, int* nt, int* persistent, int* grid_ctas);
 /* ... and how many of its K segments were fetched by the TMA engine from pre-split planes */
 int ddg_conv_last_launch_tma(void);
+int ddg_conv_last_launch_ksplit(void);   /* split-K factor of the last ddg_conv2d_fwd launch made from this thread (1 = not split) */
 
 /* Fused attention core of AttnBlockpp (layerspp.py:108-124) for 256 tokens x 256 channels (the 16x16 attention level):
  *   out = (res + NIN_3(softmax(q k^T / sqrt(C)) v) + bias) * out_scale, written PNHWC, + GroupNorm statistics of the result.

@@ -183,7 +183,7 @@ def test_layout_roundtrip_and_fir(ops):
     assert O.rel_l2(s2d[:, 1:6, 1:6, :].cpu(), cells) < 1e-5
 
 
-def _conv_case(ops, n, cin, cout, h, k, prec=3, affine=False, act=0, res=False, nchw=False, msub=0, temb=False, skip1x1=0, force_linear=0):
+def _conv_case(ops, n, cin, cout, h, k, prec=3, affine=False, act=0, res=False, nchw=False, msub=0, temb=False, skip1x1=0, force_linear=0, splitk=None):
     x = seeded((n, cin, h, h), 30)
     w = seeded((cout, cin, k, k), 31) / math.sqrt(cin * k * k)
     b = seeded((cout,), 32, 0.1)
@@ -233,7 +233,11 @@ def _conv_case(ops, n, cin, cout, h, k, prec=3, affine=False, act=0, res=False, 
         rd = ops.to_pnhwc(r.to(DEV), cpad=cout) if res else None
     ops.conv2d_fused(cw, srcs, n, h, h, out, out_mode=mode, bias=b.to(DEV), res=rd,
                      out_scale=(1 / math.sqrt(2) if res else 1.0), stats=st, msub=msub,
-                     addvec=(tv.to(DEV) if temb else None), addvec_stride=cout, force_linear=force_linear)
+                     addvec=(tv.to(DEV) if temb else None), addvec_stride=cout, force_linear=force_linear, splitk_ws=splitk)
+    if splitk is not None:
+        from ddgan_b200._lib import lib
+        assert lib().ddg_conv_last_launch_ksplit() > 1, 'expected a split-K launch'
+        assert int(splitk[:4096].view(torch.int32).abs().max()) == 0, 'arrival counters must be back at zero'
     y = out if nchw else ops.from_pnhwc(out, cout)
     err = O.rel_l2(y.cpu(), ref)
     s1 = ref.double().sum(dim=(2, 3)); s2 = (ref.double() ** 2).sum(dim=(2, 3))
@@ -263,6 +267,20 @@ def test_conv_tc_fused_variants(ops):
     # fused 1x1 skip conv as a second K segment + residual rescale (ResnetBlockBigGANpp_Adagn, layerspp.py:305-310)
     err, e1, e2 = _conv_case(ops, 4, 256, 128, 16, 3, affine=True, act=1, skip1x1=384)
     assert err < 2e-5 and e1 < 5e-5 and e2 < 5e-5, (err, e1, e2)
+
+
+@pytest.mark.parametrize('n,cin,cout,h,kw', [(64, 256, 256, 4, dict(affine=True, act=1, res=True, temb=True)),
+                                             (64, 256, 256, 4, dict(skip1x1=256, affine=True, act=1)),
+                                             (16, 512, 512, 4, dict(act=2)), (8, 256, 256, 8, dict(affine=True, act=1, res=True)),
+                                             (2, 128, 128, 16, dict(temb=True)), (64, 128, 128, 4, dict())])
+def test_conv_tc_split_k_small_levels(ops, n, cin, cout, h, kw):
+    """4x4 / 8x8 levels: a few dozen one-tile CTAs split K between 2 or 4 CTAs per tile and reduce through the workspace; same result
+    as the unsplit launch up to fp32 reassociation, statistics included; the workspace is reusable launch after launch."""
+    ws = ops.alloc_splitk_ws(DEV)
+    base = _conv_case(ops, n, cin, cout, h, 3, **kw)
+    for _ in range(2):
+        err, e1, e2 = _conv_case(ops, n, cin, cout, h, 3, splitk=ws, **kw)
+        assert err < 2e-5 and e1 < 2e-5 and e2 < 2e-5, (err, e1, e2, base)
 
 
 def test_conv_tc_linear_and_2d_tilings_agree(ops):
