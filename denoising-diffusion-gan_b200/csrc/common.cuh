@@ -74,18 +74,33 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
 // are visible.  Rules every such kernel follows here: no global memory access before pdl_wait(), and pdl_trigger() only after
 // pdl_wait() -- so a dependent kernel can overlap its direct predecessor only, never anything older.  Without the launch attribute both
 // instructions are no-ops.  Works inside stream capture (the edge becomes a programmatic dependency of the CUDA graph).
+// Compiled in only with -DDDG_ENABLE_PDL: inside the captured loops PDL measured no gain, so the default build carries neither
+// instruction and launches with the plain <<< >>> syntax.
+#ifdef DDG_ENABLE_PDL
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_trigger() {}
+#endif
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+#ifndef DDG_ENABLE_PDL
+  kern<<<grid, block, smem, stream>>>(KArgs(args)...);
+  return cudaSuccess;
+#endif
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
+#ifdef DDG_ENABLE_PDL
   cfg.numAttrs = ddg_pdl_enabled() ? 1 : 0;
+#else
+  cfg.numAttrs = 0;
+#endif
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 

@@ -238,9 +238,6 @@ constexpr int kThreads = (kProdWarps + 2) * 32;   // one tile per CTA: the produ
 constexpr int kThreadsPersist = 16 * 32;
 constexpr int kEpiWarp0 = 12;
 constexpr int kRegsProd = 168, kRegsUtil = 40, kRegsEpi = 128;   // 256*168 + 128*40 + 128*128 = 64512 <= 65536
-constexpr int kStageTile = 32 * 36;                 // one warp's epilogue staging tile (padded 32 x 32 fp32 block) ...
-constexpr int kStageFloats = kStageTile + 64;       // ... followed by its 32 row descriptors (int2)
-constexpr int kStageBytes = kStageFloats * 4;
 
 template <int MSUB, int NT, int KB, int PREC>
 struct ConvCfg {
@@ -276,7 +273,9 @@ __device__ __forceinline__ void decode_out_row(const ConvDev& p, int m, int m_en
 
 // PROF: per-role cycle counters (clock64 pairs around every barrier wait) are compiled in only for the tuning builds that
 // tools/conv_prof.py asks for through desc.debug_prof; the production instantiations carry none of that.
-template <int MSUB, int NT, int KB, int PREC, bool PERSIST, bool PROF>
+// SPLITK: separate instantiations for the split-K launches -- with the K-range tests and the partial-sum code compiled into the common
+// kernel, every one-tile launch lost 0.7-1.7 us (instruction fetch of the epilogue, dynamic source lookup at the producers' start).
+template <int MSUB, int NT, int KB, int PREC, bool PERSIST, bool PROF, bool SPLITK>
 __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvDev p) {
 #define DDG_CLK() (PROF ? clock64() : 0LL)
   using Cfg = ConvCfg<MSUB, NT, KB, PREC>;
@@ -304,11 +303,6 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
   const int a_plane = KCH * p.win_pitch;          // bytes of one A plane
   const int a_stage = a_plane * NPL;
   uint8_t* sA = sB + NSB * Cfg::B_STAGE;
-  // epilogue staging tiles (32 rows x 36 floats per warp): the producer warps run their epilogues when every MMA of the CTA has
-  // completed, so they reuse the operand rings; the dedicated epilogue warps of the persistent variant work while the next tile's
-  // mainloop owns the rings and get their own four tiles behind the A ring.
-  float* stage_ring = reinterpret_cast<float*>(sB);
-  float* stage_epi = reinterpret_cast<float*>(sA + NSA * a_stage);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -323,7 +317,7 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
   auto set_tile = [&](int tile) {
     int mx;
     if (PERSIST) { ntile = tile / p.tiles_m; mx = tile - ntile * p.tiles_m; }
-    else { mx = blockIdx.x / p.ksplit; ntile = blockIdx.y; }
+    else { mx = blockIdx.x; ntile = blockIdx.y; }
     m0 = (p.batch_rows > 0 ? blockIdx.z * p.batch_rows : 0) + mx * MT;
     m_end = p.batch_rows > 0 ? (blockIdx.z + 1) * p.batch_rows : p.Mtotal;
     if (p.tile2d) {
@@ -343,7 +337,9 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
   }
   if (warp == kProdWarps + 1) {
     tmem_alloc<TM_COLS>(smem_u32(tmem_slot));
+#ifdef DDG_ENABLE_PDL
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");   // a co-resident CTA (next kernel, PDL) may allocate
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -357,63 +353,25 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
   int nkb_total = 0;
   for (int s = 0; s < p.nsrc; ++s) nkb_total += p.src[s].C / KB;
   // split-K: this CTA's share of the K blocks (the whole range unless ksplit > 1; never in the persistent variant)
-  const int krank = PERSIST ? 0 : (int)(blockIdx.x % p.ksplit);
-  const int kb_lo = (!PERSIST && p.ksplit > 1) ? p.kb_split[krank] : 0;
-  const int kb_hi = (!PERSIST && p.ksplit > 1) ? p.kb_split[krank + 1] : nkb_total;
-  const int tile_id = PERSIST ? 0 : (int)(blockIdx.y * (gridDim.x / p.ksplit) + blockIdx.x / p.ksplit);
+  // (the rank is blockIdx.z: the K-range tests of the single-thread roles stay in uniform registers)
+  static_assert(!(SPLITK && PERSIST), "split-K is a one-tile-per-CTA mode");
+  const int krank = SPLITK ? (int)blockIdx.z : 0;
+  const int kb_lo = SPLITK ? p.kb_split[krank] : 0;
+  const int kb_hi = SPLITK ? p.kb_split[krank + 1] : nkb_total;
+  const int tile_id = SPLITK ? (int)(blockIdx.y * gridDim.x + blockIdx.x) : 0;
 
   // =================================== epilogue (one tile) ===================================
   // quad: TMEM lane quadrant of the calling warp; the warp handles column chunks half0, half0 + hstep, ...
   // it: tile iteration of this CTA (selects the accumulator set and the barrier parity).
   // wait_acc = false: the caller has already established that the tile's MMAs completed (see the producers' helper call)
-  // The epilogue is written for SMALL CODE first: an ncu source view of the first version (row-per-thread, every loop unrolled,
-  // ~9.6k SASS instructions executed a handful of times per tile) showed its warps stalled on instruction fetch (stall_no_inst on
-  // almost every sample) -- a 128 x 256 tile cost ~36k cycles, as long as the BF16x3 mainloop of the same tile.  Now the 32 x 32 block
-  // a warp reads from TMEM (lane = pixel row, register = channel) goes through a padded shared-memory staging tile and two rolled loops
-  // work from there:
-  //   fast path (32-column chunks inside Cout, NHWC / padded-NHWC output): 8 lanes per pixel (lane = 4 channels), 4 pixels per
-  //     instruction -> every global load / store of the warp covers 4 x 128 contiguous bytes (4 memory wavefronts instead of 32), and the
-  //     GroupNorm statistics are summed over a lane's 8 pixels in registers first (16 shuffles per chunk instead of 62);
-  //   slow path (NCHW output, Cout tails, N = 16 tiles): one thread per pixel row, one column per iteration (coalesced for NCHW).
-  // stg: this warp's staging area = 32 rows x 36 floats, then 32 x int2 row descriptors (pixel index, sample | invalid << 31).
-  // own_stage: stg is private to this warp (persistent epilogue warps); the producers' tiles alias the operand rings and may only be
-  // touched once the accumulator barrier says that every MMA of the tile has completed.
-  auto run_epilogue = [&](int it, int quad, int half0, int hstep, bool release, bool wait_acc, float* stg, bool own_stage) {
+  auto run_epilogue = [&](int it, int quad, int half0, int hstep, bool release, bool wait_acc) {
     const int ab = PERSIST ? (it & 1) : 0;
-    constexpr int CW = (NT >= 64) ? 32 : 16;         // columns per tcgen05.ld
-    constexpr int NCHUNK = NT / CW;
-    constexpr int NU = MSUB * NCHUNK;                 // work units = (sub-tile, column chunk) pairs, dealt round-robin to the warps
-                                                      // that share this lane quadrant
-    const int rq = lane >> 3;                         // fast path: this lane's pixel row inside each group of 4 rows
-    const int c4 = (lane & 7) * 4;                    // ... and its 4 channels inside the 32-column chunk
-    int2* rinfo = reinterpret_cast<int2*>(stg + kStageTile);
-    int sub_cur = -1;
-    bool valid = false; int n = 0, h = 0, w = 0;      // this thread's own pixel row (row descriptors, slow path)
-    uint32_t pix = 0;
-    int n_first = 0, n_last = 0;
-    auto load_rows = [&](int sub) {
-      sub_cur = sub;
-      const int ml = sub * 128 + quad * 32 + lane;
-      if (p.tile2d) {
-        n = t2_n; h = t2_y0 + (ml >> 3); w = t2_x0 + (ml & 7);
-        valid = (h < p.Hout) && (w < p.Wout);
-      } else {
-        decode_out_row(p, m0 + ml, m_end, valid, n, h, w);
-      }
-      pix = (p.out_mode == 0) ? (uint32_t)((n * (p.Hout + 2) + h + 1) * (p.Wout + 2) + (w + 1)) : (uint32_t)((n * p.Hout + h) * p.Wout + w);
-      __syncwarp();                                   // readers of the previous descriptors are done
-      rinfo[lane] = make_int2((int)pix, valid ? n : (n | (int)0x80000000));
-      n_first = __shfl_sync(0xffffffffu, n, 0);
-      n_last = __shfl_sync(0xffffffffu, n, 31);
-      __syncwarp();
-    };
-    if (own_stage && half0 < NU) load_rows(half0 / NCHUNK);   // (before the wait: overlaps the end of the mainloop)
     if (wait_acc) mbar_wait(accFull(ab), PERSIST ? ((it >> 1) & 1) : 0);
     tc_fence_after();
     // split-K: ranks 0 .. ksplit-2 only park their partial accumulators; the last rank (highest block index of the tile, so that
     // in-order CTA dispatch has put its writers on the machine before it) waits for them and adds them before the usual epilogue.
-    const bool sk_writer = !PERSIST && p.ksplit > 1 && krank < p.ksplit - 1;
-    const bool sk_reduce = !PERSIST && p.ksplit > 1 && krank == p.ksplit - 1;
+    const bool sk_writer = SPLITK && krank < p.ksplit - 1;
+    const bool sk_reduce = SPLITK && krank == p.ksplit - 1;
     if (sk_reduce) {
       if (lane == 0) {
         const unsigned want = (unsigned)(p.ksplit - 1) * kProdWarps;     // one arrival per epilogue warp of every writer CTA
@@ -421,33 +379,36 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
       }
       __syncwarp();
     }
-#pragma unroll 1
-    for (int u = half0; u < NU; u += hstep) {
-      const int sub = u / NCHUNK, ck = u - sub * NCHUNK;
-      const int col0 = ntile * NT + ck * CW;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * ACC_COLS + sub * NT + ck * CW);
-      if (col0 >= p.Cout) continue;
-      if (sub != sub_cur && !sk_writer) load_rows(sub);
-      const bool fast = (CW == 32) && (p.out_mode != 2) && (col0 + CW <= p.Cout);
-      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), av0 = b4, av1 = b4;
-      float4 rs[4];
-      {
-        float v[CW];
-        if (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
-        if (CW == 32 && fast && !sk_writer) {
-          // operands that do not depend on the accumulators are put in flight before the TMEM wait
-          if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c4));
-          if (p.addvec) {
-            av0 = __ldg(reinterpret_cast<const float4*>(p.addvec + (size_t)n_first * p.addvec_stride + col0 + c4));
-            av1 = __ldg(reinterpret_cast<const float4*>(p.addvec + (size_t)n_last * p.addvec_stride + col0 + c4));
+    constexpr int CW = (NT >= 64) ? 32 : 16;         // columns per tcgen05.ld
+    constexpr int NCHUNK = NT / CW;
+    // work units = (sub-tile, column chunk) pairs, dealt round-robin to the warps that share this lane quadrant
+    int sub_prev = -1;
+    bool valid = false; int n = 0, h = 0, w = 0;
+    size_t obase = 0;
+    int n_first = 0, n_last = 0;
+    {
+      for (int u = half0; u < MSUB * NCHUNK; u += hstep) {
+        const int sub = u / NCHUNK, ck = u - sub * NCHUNK;
+        if (sub != sub_prev) {
+          sub_prev = sub;
+          const int m = m0 + sub * 128 + quad * 32 + lane;
+          if (p.tile2d) {
+            const int ml = sub * 128 + quad * 32 + lane;
+            n = t2_n; h = t2_y0 + (ml >> 3); w = t2_x0 + (ml & 7);
+            valid = (h < p.Hout) && (w < p.Wout);
+          } else {
+            decode_out_row(p, m, m_end, valid, n, h, w);
           }
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            rs[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const int2 ri = rinfo[kk * 4 + rq];
-            if (p.res && ri.y >= 0) rs[kk] = __ldg(reinterpret_cast<const float4*>(p.res + (size_t)(uint32_t)ri.x * p.out_C + col0 + c4));
-          }
+          obase = 0;
+          if (p.out_mode == 0) obase = ((size_t)(n * (p.Hout + 2) + h + 1) * (p.Wout + 2) + (w + 1)) * p.out_C;
+          else if (p.out_mode == 1) obase = ((size_t)(n * p.Hout + h) * p.Wout + w) * p.out_C;
+          n_first = __shfl_sync(0xffffffffu, n, 0);
+          n_last = __shfl_sync(0xffffffffu, n, 31);
         }
+        const int col0 = ntile * NT + ck * CW;
+        float v[CW];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * ACC_COLS + sub * NT + ck * CW);
+        if (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
         tmem_ld_wait();
         if (sk_writer || sk_reduce) {
           const size_t prow = (size_t)(sub * 128 + quad * 32 + lane) * NT + ck * CW;   // thread = accumulator row: 128 contiguous bytes
@@ -467,114 +428,125 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
             }
           }
         }
-        __syncwarp();                                  // the previous unit has been read out of the staging tile
-        float4* s4 = reinterpret_cast<float4*>(stg + lane * 36);   // pitch 36 floats: the 8 lanes of a store phase hit 32 distinct banks
+        if (col0 < p.Cout) {
+          const bool full = (col0 + CW <= p.Cout);
+          if (full) {
+            // vectorised per-channel bias and per-(sample, channel) add (Dense_0(temb) / dense_t1)
+            if (p.bias) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-        for (int j = 0; j < CW / 4; ++j) s4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-      }
-      __syncwarp();
-      if (CW == 32 && fast) {
-        float sa1[4] = {0.f, 0.f, 0.f, 0.f}, sa2[4] = {0.f, 0.f, 0.f, 0.f};   // sum / sum of squares, rows of sample n_first
-        float sb1[4] = {0.f, 0.f, 0.f, 0.f}, sb2[4] = {0.f, 0.f, 0.f, 0.f};   // ... rows of sample n_last (when the warp spans two)
-        const float osc = p.out_scale;
-        const size_t img = (size_t)(p.Hout + 2) * (p.Wout + 2);
-#pragma unroll 1
-        for (int g = 0; g < 2; ++g) {
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const int r = g * 16 + kk * 4 + rq;
-            const int2 ri = rinfo[r];
-            float4 y = *reinterpret_cast<const float4*>(stg + r * 36 + c4);
-            const int nr = ri.y & 0x7fffffff;
-            const bool isA = (nr == n_first);
-            float4 av = isA ? av0 : av1;
-            if (p.addvec && !isA && nr != n_last)      // a warp that spans more than two samples (1x1 / 2x2 images): fetch the row's own vector
-              av = __ldg(reinterpret_cast<const float4*>(p.addvec + (size_t)nr * p.addvec_stride + col0 + c4));
-            y.x += b4.x + av.x + rs[kk].x; y.y += b4.y + av.y + rs[kk].y;
-            y.z += b4.z + av.z + rs[kk].z; y.w += b4.w + av.w + rs[kk].w;
-            if (g == 0) {                              // residual rows of the second half: in flight while the first half is stored
-              rs[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
-              const int2 rj = rinfo[r + 16];
-              if (p.res && rj.y >= 0) rs[kk] = __ldg(reinterpret_cast<const float4*>(p.res + (size_t)(uint32_t)rj.x * p.out_C + col0 + c4));
-            }
-            if (ri.y >= 0) {
-              const size_t o = (size_t)(uint32_t)ri.x * p.out_C + col0 + c4;
-              if (p.out_act == ACT_TANH) { y.x = tanhf(y.x * osc); y.y = tanhf(y.y * osc); y.z = tanhf(y.z * osc); y.w = tanhf(y.w * osc); }
-              else { y.x *= osc; y.y *= osc; y.z *= osc; y.w *= osc; }
-              *reinterpret_cast<float4*>(p.out + o) = y;
-              if (p.out_planes != nullptr && p.out_mode == 0) {
-                // the same values once more as bf16 hi / lo planes [n][chunk][h+1][w+1][8]: consumers that take this tensor without a
-                // prologue fetch them with the TMA engine instead of converting fp32 in their producer warps
-                uint2 hi, lo;
-                split_bf16x2(y.x, y.y, hi.x, lo.x); split_bf16x2(y.z, y.w, hi.y, lo.y);
-                const size_t pxl = (size_t)(uint32_t)ri.x - (size_t)nr * img;
-                const size_t off = (((size_t)nr * (p.out_C / 8) + ((col0 + c4) >> 3)) * img + pxl) * 16 + ((c4 & 4) ? 8 : 0);
-                uint8_t* pb = reinterpret_cast<uint8_t*>(p.out_planes);
-                *reinterpret_cast<uint2*>(pb + off) = hi;
-                if (NPL == 2) *reinterpret_cast<uint2*>(pb + p.out_plane_bytes + off) = lo;
+              for (int j = 0; j < CW / 4; ++j) {
+                const float4 b = __ldg(b4 + j);
+                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
               }
-              if (isA) {
-                sa1[0] += y.x; sa1[1] += y.y; sa1[2] += y.z; sa1[3] += y.w;
-                sa2[0] += y.x * y.x; sa2[1] += y.y * y.y; sa2[2] += y.z * y.z; sa2[3] += y.w * y.w;
-              } else {
-                sb1[0] += y.x; sb1[1] += y.y; sb1[2] += y.z; sb1[3] += y.w;
-                sb2[0] += y.x * y.x; sb2[1] += y.y * y.y; sb2[2] += y.z * y.z; sb2[3] += y.w * y.w;
+            }
+            if (p.addvec) {
+              const float4* a4 = reinterpret_cast<const float4*>(p.addvec + (size_t)n * p.addvec_stride + col0);
+#pragma unroll
+              for (int j = 0; j < CW / 4; ++j) {
+                const float4 b = __ldg(a4 + j);
+                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CW; ++j) {
+              const int cc = col0 + j;
+              if (cc < p.Cout) {
+                if (p.bias) v[j] += __ldg(p.bias + cc);
+                if (p.addvec) v[j] += __ldg(p.addvec + (size_t)n * p.addvec_stride + cc);
               }
             }
           }
-        }
-        if (p.stats) {
-          // per-(n, channel) sum and sum of squares of the stored values: lanes l, l^8, l^16, l^24 hold the same 4 channels
-#pragma unroll 1
-          for (int pass = 0; pass < 2; ++pass) {
-            if (pass == 1) {
-              if (n_last == n_first) break;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) { sa1[j] = sb1[j]; sa2[j] = sb2[j]; }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              sa1[j] += __shfl_xor_sync(0xffffffffu, sa1[j], 8); sa1[j] += __shfl_xor_sync(0xffffffffu, sa1[j], 16);
-              sa2[j] += __shfl_xor_sync(0xffffffffu, sa2[j], 8); sa2[j] += __shfl_xor_sync(0xffffffffu, sa2[j], 16);
-            }
-            // every lane publishes one channel: c4 + rq
-            const float m1 = rq == 0 ? sa1[0] : (rq == 1 ? sa1[1] : (rq == 2 ? sa1[2] : sa1[3]));
-            const float m2 = rq == 0 ? sa2[0] : (rq == 1 ? sa2[1] : (rq == 2 ? sa2[2] : sa2[3]));
-            double* dst = p.stats + ((size_t)(pass == 0 ? n_first : n_last) * p.Cout + col0 + c4 + rq) * 2;
-            atomicAdd(dst, (double)m1);
-            atomicAdd(dst + 1, (double)m2);
-          }
-        }
-      } else {
-        // ---------------- slow path: one thread per pixel row, one column per iteration ----------------
-#pragma unroll 1
-        for (int j = 0; j < CW; ++j) {
-          const int cc = col0 + j;
-          if (cc >= p.Cout) break;
-          float y = stg[lane * 36 + j];
-          if (p.bias) y += __ldg(p.bias + cc);
-          if (p.addvec) y += __ldg(p.addvec + (size_t)n * p.addvec_stride + cc);
           if (valid) {
-            const size_t oi = (p.out_mode == 2) ? ((size_t)(n * p.Cout + cc) * p.Hout + h) * p.Wout + w : (size_t)pix * p.out_C + cc;
-            if (p.res) y += __ldg(p.res + oi);
-            y = apply_act(y * p.out_scale, p.out_act);
-            p.out[oi] = y;
+            if (p.out_mode != 2) {
+              if (p.res) {
+                const float4* r4 = reinterpret_cast<const float4*>(p.res + obase + col0);
+#pragma unroll
+                for (int j = 0; j < CW / 4; ++j) {
+                  const float4 r = __ldg(r4 + j);
+                  v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+                }
+              }
+              const float osc = p.out_scale;
+              if (p.out_act == ACT_TANH) {
+#pragma unroll
+                for (int j = 0; j < CW; ++j) v[j] = tanhf(v[j] * osc);
+              } else {
+#pragma unroll
+                for (int j = 0; j < CW; ++j) v[j] *= osc;
+              }
+              float4* o4 = reinterpret_cast<float4*>(p.out + obase + col0);
+#pragma unroll
+              for (int j = 0; j < CW / 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (p.out_planes != nullptr && full && p.out_mode == 0) {
+                // the same values once more as bf16 hi / lo planes [n][chunk][h+1][w+1][8]: consumers that take this tensor without a
+                // prologue (1x1 skip convs) fetch them with the TMA engine instead of converting fp32 in their producer warps
+                const size_t img = (size_t)(p.Hout + 2) * (p.Wout + 2);
+                const size_t pix = (size_t)(h + 1) * (p.Wout + 2) + (w + 1);
+                uint8_t* pb = reinterpret_cast<uint8_t*>(p.out_planes);
+#pragma unroll
+                for (int q = 0; q < CW / 8; ++q) {
+                  uint4 hi, lo;
+                  split_bf16x2(v[8 * q], v[8 * q + 1], hi.x, lo.x); split_bf16x2(v[8 * q + 2], v[8 * q + 3], hi.y, lo.y);
+                  split_bf16x2(v[8 * q + 4], v[8 * q + 5], hi.z, lo.z); split_bf16x2(v[8 * q + 6], v[8 * q + 7], hi.w, lo.w);
+                  const size_t off = (((size_t)n * (p.out_C / 8) + (col0 / 8 + q)) * img + pix) * 16;
+                  *reinterpret_cast<uint4*>(pb + off) = hi;
+                  if (NPL == 2) *reinterpret_cast<uint4*>(pb + p.out_plane_bytes + off) = lo;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) {
+                const int cc = col0 + j;
+                if (cc < p.Cout) {
+                  const size_t oi = ((size_t)(n * p.Cout + cc) * p.Hout + h) * p.Wout + w;
+                  float y = v[j];
+                  if (p.res) y += __ldg(p.res + oi);
+                  y = apply_act(y * p.out_scale, p.out_act);
+                  v[j] = y;
+                  p.out[oi] = y;
+                }
+              }
+            }
           }
           if (p.stats) {
-#pragma unroll 1
+            // per-(n, channel) sum and sum of squares of the stored values; lanes = rows, registers = channels.
             for (int pass = 0; pass < 2; ++pass) {
               const int n_sel = pass == 0 ? n_first : n_last;
               if (pass == 1 && n_last == n_first) break;
-              float y1 = (valid && n == n_sel) ? y : 0.f, y2 = y1 * y1;
+              const bool mine = valid && (n == n_sel);
+              float s1[CW], s2[CW];
+#pragma unroll
+              for (int j = 0; j < CW; ++j) { const float y = mine ? v[j] : 0.f; s1[j] = y; s2[j] = y * y; }
+              // transpose-reduce over the 32 lanes: afterwards lane L holds column (L % CW) totals in s1[0]/s2[0]
 #pragma unroll
               for (int sft = 16; sft >= 1; sft >>= 1) {
-                y1 += __shfl_xor_sync(0xffffffffu, y1, sft);
-                y2 += __shfl_xor_sync(0xffffffffu, y2, sft);
+                if (sft < CW) {
+                  const bool up = (lane & sft) != 0;
+#pragma unroll
+                  for (int i = 0; i < sft; ++i) {
+                    const float a1 = up ? s1[i] : s1[i + sft];
+                    const float b1 = up ? s1[i + sft] : s1[i];
+                    s1[i] = b1 + __shfl_xor_sync(0xffffffffu, a1, sft);
+                    const float a2 = up ? s2[i] : s2[i + sft];
+                    const float b2 = up ? s2[i + sft] : s2[i];
+                    s2[i] = b2 + __shfl_xor_sync(0xffffffffu, a2, sft);
+                  }
+                } else {
+                  // CW == 16 and sft == 16: plain butterfly add of all 16 columns
+#pragma unroll
+                  for (int i = 0; i < CW; ++i) {
+                    s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], sft);
+                    s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], sft);
+                  }
+                }
               }
-              if (lane == 0) {
+              const int cc = col0 + (lane % CW);
+              if (cc < p.Cout && (CW == 32 || lane < 16)) {
                 double* dst = p.stats + ((size_t)n_sel * p.Cout + cc) * 2;
-                atomicAdd(dst, (double)y1);
-                atomicAdd(dst + 1, (double)y2);
+                atomicAdd(dst, (double)s1[0]);
+                atomicAdd(dst + 1, (double)s2[0]);
               }
             }
           }
@@ -704,7 +676,7 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
     float cur[IMAX][8], nxt[IMAX][8];
     int off_c[IMAX], nn_c[IMAX], off_n[IMAX], nn_n[IMAX];
     int s_cur = 0, kb_cur = kb_lo;                     // (source, K block inside it) of the first K block of this CTA
-    while (kb_cur >= p.src[s_cur].C / KB) { kb_cur -= p.src[s_cur].C / KB; ++s_cur; }
+    if (SPLITK) { while (kb_cur >= p.src[s_cur].C / KB) { kb_cur -= p.src[s_cur].C / KB; ++s_cur; } }
     if (!p.src[s_cur].tma) {
       int lo_, hi_;
       src_rows(p.src[s_cur], lo_, hi_);
@@ -813,9 +785,9 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
     pdl_trigger();
     if (!PERSIST) {
       const long long t_prod1 = DDG_CLK();
-      if (PROF) mbar_wait(accFull(0), 0);          // (counter builds only: run_epilogue waits itself, after prefetching its first operands)
+      mbar_wait(accFull(0), 0);
       const long long t_epi0 = DDG_CLK();
-      run_epilogue(0, warp & 3, warp >> 2, 2, true, true, stage_ring + warp * kStageFloats, false);
+      run_epilogue(0, warp & 3, warp >> 2, 2, true, true);
       if (prof_on && tid == 0) {
         p.prof[0] = t_prod1 - t_prod0;   // producer loop total
         p.prof[1] = w_emptyA;            // ... of which waiting for a free A stage
@@ -836,7 +808,7 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
     // last tile -- has completed, which is exactly the condition for reading the accumulators.
     if (PERSIST && it > 0) {
       mbar_wait(emptyA(last_st), last_ph);
-      run_epilogue(it - 1, warp & 3, 1 + (warp >> 2), 3, false, false, stage_ring + warp * kStageFloats, false);
+      run_epilogue(it - 1, warp & 3, 1 + (warp >> 2), 3, false, false);
     }
   } else if (warp < kEpiWarp0) {
     // WG2: the two single-thread roles (+ two idle warps in the persistent layout); their registers go to the producers
@@ -857,7 +829,7 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
         for (int s = 0; s < p.nsrc; ++s) {
           const SrcDev& S = p.src[s];
           for (int kb = 0; kb < S.C / KB; ++kb, ++kbi) {
-            if (kbi < kb_lo || kbi >= kb_hi) { i += S.ntaps; continue; }     // another CTA's share of K (split-K)
+            if (SPLITK && (kbi < kb_lo || kbi >= kb_hi)) { i += S.ntaps; continue; }     // another CTA's share of K (split-K)
             mbar_wait(emptyA(stA_l), phA_l ^ 1);
             if (S.tma) {
               // halo window (16*MSUB+2 rows x 10 columns) x 4 chunks of 8 channels, from the padded planes [n][chunk][y][x][8]
@@ -915,7 +887,7 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
       int s_m = 0, kb_m = 0;
       for (int kb_idx = 0; kb_idx < nkb_total; ++kb_idx) {
         const SrcDev& S = p.src[s_m];
-        if (kb_idx < kb_lo || kb_idx >= kb_hi) {        // another CTA's share of K (split-K)
+        if (SPLITK && (kb_idx < kb_lo || kb_idx >= kb_hi)) {        // another CTA's share of K (split-K)
           if (++kb_m >= S.C / KB) { kb_m = 0; ++s_m; }
           continue;
         }
@@ -987,8 +959,8 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
     for (int tile = tile_first; tile < tile_end; tile += tile_stride, ++it) {
       set_tile(tile);
       const bool last = tile + tile_stride >= tile_end;
-      if (PROF) { const long long tw = DDG_CLK(); mbar_wait(accFull(it & 1), (it >> 1) & 1); w_accF += DDG_CLK() - tw; }
-      run_epilogue(it, warp & 3, 0, last ? 3 : 1, true, true, stage_epi + (warp - kEpiWarp0) * kStageFloats, true);
+      { const long long tw = DDG_CLK(); mbar_wait(accFull(it & 1), (it >> 1) & 1); w_accF += DDG_CLK() - tw; }
+      run_epilogue(it, warp & 3, 0, last ? 3 : 1, true, true);
     }
     if (PROF && p.prof != nullptr && blockIdx.x == gridDim.x / 2 && warp == kEpiWarp0 && lane == 0) {
       p.prof[11] = DDG_CLK() - t_e0;   // epilogue warps: whole tile loop
@@ -997,7 +969,7 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
   }
 
   __syncthreads();
-  if (!PERSIST && p.ksplit > 1 && krank == p.ksplit - 1 && threadIdx.x == 0) p.ws_flag[tile_id] = 0u;   // ready for the next launch
+  if (SPLITK && krank == p.ksplit - 1 && threadIdx.x == 0) p.ws_flag[tile_id] = 0u;   // ready for the next launch
   if (warp == kProdWarps + 1) {
     tc_fence_after();
     tmem_dealloc<TM_COLS>(tmem_base);
@@ -1083,11 +1055,11 @@ static bool valid_nt(int nt) { return nt == 16 || nt == 64 || nt == 128 || nt ==
 
 static int g_nsa_max = getenv("DDG_CONV_NSA") ? atoi(getenv("DDG_CONV_NSA")) : 4;
 
-template <int MSUB, int NT, int KB, int PREC, bool PERSIST = false, bool PROF = false>
+template <int MSUB, int NT, int KB, int PREC, bool PERSIST = false, bool PROF = false, bool SPLITK = false>
 static int launch_conv(ConvDev& d, int n_tiles, cudaStream_t stream) {
   using Cfg = ConvCfg<MSUB, NT, KB, PREC>;
   const size_t a_stage = (size_t)Cfg::NPL * Cfg::KCH * d.win_pitch;
-  const size_t fixed = 256 + (size_t)Cfg::NSB * Cfg::B_STAGE + (PERSIST ? 4 * kStageBytes : 0);
+  const size_t fixed = 256 + (size_t)Cfg::NSB * Cfg::B_STAGE;
   if (fixed + 2 * a_stage > 227 * 1024) { ddg_set_last_error("conv_tc: shared memory budget exceeded"); return DDG_ERR_UNSUPPORTED; }
   // A ring: as deep as the budget allows, up to 4 stages (1-tap K segments consume a stage in ~12 MMAs: two stages cannot hide the
   // load -> convert -> store latency of the producers)
@@ -1096,9 +1068,8 @@ static int launch_conv(ConvDev& d, int n_tiles, cudaStream_t stream) {
   if (nsa < 2) nsa = 2;
   if (nsa > 4) nsa = 4;
   d.nsa = nsa;
-  size_t smem = fixed + (size_t)nsa * a_stage;
-  if (smem < 256 + (size_t)kProdWarps * kStageBytes) smem = 256 + (size_t)kProdWarps * kStageBytes;   // staging tiles of the producers' epilogue
-  auto kern = conv_tc_kernel<MSUB, NT, KB, PREC, PERSIST, PROF>;
+  const size_t smem = fixed + (size_t)nsa * a_stage;
+  auto kern = conv_tc_kernel<MSUB, NT, KB, PREC, PERSIST, PROF, SPLITK>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1116,8 +1087,8 @@ static int launch_conv(ConvDev& d, int n_tiles, cudaStream_t stream) {
     grid = dim3((unsigned)(total < num_sms() ? total : num_sms()));
     g_last_info[3] = (int)grid.x;
     d.ksplit = 1;
-  } else if (d.ksplit > 1) {
-    grid.x *= d.ksplit;                   // the ksplit CTAs of a tile are neighbours in block order
+  } else if (SPLITK) {
+    grid.z = d.ksplit;                    // rank = blockIdx.z: every writer rank is dispatched before the reducing rank (z = ksplit - 1)
     g_last_info[3] *= d.ksplit;
   }
   launch_pdl(kern, grid, dim3(PERSIST ? kThreadsPersist : kThreads), smem, stream, d);
@@ -1373,7 +1344,7 @@ extern "C" int ddg_conv2d_fwd(const ddg_conv_desc* c, cudaStream_t stream) {
   // split-K for grids that leave most of the machine idle (4x4 / 8x8 levels: a few dozen one-tile CTAs, each a serial chain of
   // K/16 * 3 MMAs): ksplit CTAs per tile, all resident at once (tiles * ksplit <= SMs), reduction through the caller's workspace.
   d.ksplit = 1;
-  if (g_splitk && !persist && c->splitk_ws != nullptr && c->batch_rows == 0 && nt >= 64 && c->debug_prof == nullptr) {
+  if (g_splitk && !persist && msub == 1 && (nt == 64 || nt == 128) && c->splitk_ws != nullptr && c->batch_rows == 0 && c->debug_prof == nullptr) {
     const long tiles = (tile2d ? (long)d.N * (d.Hout / (16 * msub)) * (d.Wout / 8) : ((long)d.Mtotal + MT - 1) / MT) * n_tiles;
     int nkb = 0;
     for (int s = 0; s < c->nsrc; ++s) nkb += c->src[s].C / KB;
@@ -1427,6 +1398,11 @@ extern "C" int ddg_conv2d_fwd(const ddg_conv_desc* c, cudaStream_t stream) {
     }
   }
 #undef DDG_LAUNCH_P
+  if (d.ksplit > 1) {       // (msub == 1, nt 64 / 128: see the eligibility test above)
+    if (prec == 3) { if (nt == 64) return launch_conv<1, 64, 32, 3, false, false, true>(d, n_tiles, stream); return launch_conv<1, 128, 32, 3, false, false, true>(d, n_tiles, stream); }
+    if (nt == 64) return launch_conv<1, 64, 32, 1, false, false, true>(d, n_tiles, stream);
+    return launch_conv<1, 128, 32, 1, false, false, true>(d, n_tiles, stream);
+  }
 #define DDG_LAUNCH(MS, NTV, PR) return launch_conv<MS, NTV, 32, PR>(d, n_tiles, stream)
   if (prec == 3) {
     if (nt == 256) { if (msub == 2) DDG_LAUNCH(2, 256, 3); else DDG_LAUNCH(1, 256, 3); }

@@ -122,7 +122,9 @@ int ddg_spatial_sum(const float* x, float* out, int N, int H, int W, int C, int 
  * just its border cleared to serve as the zero padding of the next 3x3 conv (ncsnpp convs use padding=1, layerspp.py:33) */
 /* Programmatic dependent launch (CUDA PDL) for the kernels of the generator / discriminator forward path: a kernel's CTAs are
  * scheduled and set up while its predecessor on the stream drains, and block (griddepcontrol.wait) before their first global access.
- * Off by default (environment DDG_PDL=1 turns it on: it measured neutral on the captured loops); returns the previous setting.  No reference counterpart: the reference's
+ * Only effective in a library built with -DDDG_ENABLE_PDL (the default build leaves the griddepcontrol instructions out: no gain
+ * measured inside the captured loops, and the bare wait instruction cost ~2 %); off by default even then (DDG_PDL=1); returns the
+ * previous setting.  No reference counterpart: the reference's
  * launches are PyTorch's. */
 int ddg_set_pdl(int on);
 int ddg_zero_border(float* buf, int N, int H, int W, int C, cudaStream_t stream);
