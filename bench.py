@@ -27,6 +27,9 @@ import sys
 import threading
 import time
 
+# stdout carries exactly one JSON line: anything NCCL wants to say (its version banner under NCCL_DEBUG=VERSION / INFO) goes to stderr
+os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, 'denoising-diffusion-gan_b200')
 for p in (ROOT, PKG):
