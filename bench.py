@@ -544,10 +544,9 @@ def run_microbench(ctx):
         b = torch.randn(C, device=dev)
         rows.append(('fused_leaky_relu', C, H, 8.0 * numel, timeit(lambda: ops.fused_bias_act(x4, b, None, 3, 0, 0.2, 2 ** 0.5))))
         xb = x.to(torch.bfloat16); xb4 = xb.view(N, C, H, H)
-        if (C, H) == (128, 128):
-            # the 16-bit upfirdn2d is a functional path (fp16 / bf16 tensors are accepted as in the reference); it has none of the
-            # fp32 entry's specialised kernels yet, one row keeps that visible
-            rows.append(('upfirdn2d_down2_bf16', C, H, 2 * numel * 1.25, timeit(lambda: ops.upfirdn2d_raw(xb, k4, 1, 1, 2, 2, 1, 1, 1, 1))))
+        # 16-bit I/O (fp16 / bf16 tensors are accepted as in the reference): register-tiled x2 kernels, fp32 taps and accumulation
+        rows.append(('upfirdn2d_down2_bf16', C, H, 2 * numel * 1.25, timeit(lambda: ops.upfirdn2d_raw(xb, k4, 1, 1, 2, 2, 1, 1, 1, 1))))
+        rows.append(('upfirdn2d_up2_bf16', C, H, 2 * numel * 5.0, timeit(lambda: ops.upfirdn2d_raw(xb, k4 * 4, 2, 2, 1, 1, 2, 1, 2, 1))))
         rows.append(('fused_leaky_relu_bf16', C, H, 4.0 * numel, timeit(lambda: ops.fused_bias_act(xb4, b, None, 3, 0, 0.2, 2 ** 0.5))))
         del xb, xb4
         G = min(C // 4, 32)

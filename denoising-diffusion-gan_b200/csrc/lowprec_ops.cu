@@ -103,9 +103,146 @@ __global__ void __launch_bounds__(256) upfirdn2d_lp_kernel(const T* __restrict__
   }
 }
 
+// ---- register-tiled fast paths for the two resampling shapes the models use (4x4 taps, in_w % 8 == 0, 16-byte aligned planes) ----
+// Same scheme as the fp32 kernels of upfirdn2d.cu, at 8 elements (16 bytes) per load: no shared memory, one 16-byte load per input
+// row per thread plus the two edge neighbours, fp32 taps / accumulation.
+template <typename T>
+__device__ __forceinline__ void lp_load_row8(const T* __restrict__ row, bool rok, bool has_l, bool has_r, float (&v)[10]) {
+  uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+  if (rok) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "l"(row));
+  const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[1 + j] = to_f<T>(e[j]);
+  v[0] = (rok && has_l) ? to_f<T>(__ldg(row - 1)) : 0.f;
+  v[9] = (rok && has_r) ? to_f<T>(__ldg(row + 8)) : 0.f;
+}
+
+// down = 2, pad = (1, 1) (downsample_2d, up_or_down_sampling.py:240-257): thread = 4 output columns x 4 output rows
+template <typename T>
+__global__ void __launch_bounds__(256) lp_k4_down2_kernel(const T* __restrict__ x, const float* __restrict__ k, T* __restrict__ out, long planes,
+                                                         int in_h, int in_w, int out_h, int out_w) {
+  constexpr int RB = 4, NR = (RB - 1) * 2 + 4;
+  float kf[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) kf[i][j] = __ldg(k + (3 - i) * 4 + (3 - j));
+  const int hb = (out_h + RB - 1) / RB;
+  const int wg = in_w >> 3;
+  const long total = planes * hb * wg;
+  const long in_plane = (long)in_h * in_w, out_plane = (long)out_h * out_w;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % wg);
+    long r = idx / wg;
+    const int oy0 = (int)(r % hb) * RB;
+    const long pl = r / hb;
+    const T* xin = x + pl * in_plane;
+    const int by = oy0 * 2 - 1, x0 = 8 * g;
+    float acc[RB][4];
+#pragma unroll
+    for (int q = 0; q < RB; ++q)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[q][c] = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < NR; ++rr) {
+      const int iy = by + rr;
+      const bool rok = (iy >= 0) && (iy < in_h);
+      float v[10];   // columns x0-1 .. x0+8
+      lp_load_row8<T>(xin + (long)(rok ? iy : 0) * in_w + x0, rok, x0 > 0, x0 + 8 < in_w, v);
+#pragma unroll
+      for (int q = 0; q < RB; ++q) {
+        const int i = rr - q * 2;
+        if (i >= 0 && i < 4) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            acc[q][c] = fmaf(v[2 * c], kf[i][0], fmaf(v[2 * c + 1], kf[i][1], fmaf(v[2 * c + 2], kf[i][2], fmaf(v[2 * c + 3], kf[i][3], acc[q][c]))));
+        }
+      }
+    }
+    T* o = out + pl * out_plane + (long)oy0 * out_w + 4 * g;
+#pragma unroll
+    for (int q = 0; q < RB; ++q)
+      if (oy0 + q < out_h) {
+        T pk[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) pk[c] = from_f<T>(acc[q][c]);
+        *reinterpret_cast<uint2*>(o + (long)q * out_w) = *reinterpret_cast<const uint2*>(pk);
+      }
+  }
+}
+
+// up = 2, pad = (2, 1) (upsample_2d, up_or_down_sampling.py:213-237), polyphase: thread = 8 input columns of one input row ->
+// 16 output columns x 2 output rows (two 32-byte stores)
+template <typename T>
+__global__ void __launch_bounds__(256) lp_k4_up2_kernel(const T* __restrict__ x, const float* __restrict__ k, T* __restrict__ out, long planes,
+                                                       int in_h, int in_w) {
+  float kf[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) kf[i][j] = __ldg(k + (3 - i) * 4 + (3 - j));
+  const int wg = in_w >> 3;
+  const long total = planes * in_h * wg;
+  const int out_w = 2 * in_w;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % wg);
+    long r = idx / wg;
+    const int yy = (int)(r % in_h);
+    const long pl = r / in_h;
+    const int x0 = 8 * g;
+    const T* xin = x + pl * (long)in_h * in_w;
+    float v[3][10];   // rows yy-1 .. yy+1, columns x0-1 .. x0+8
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int iy = yy + dy - 1;
+      const bool rok = iy >= 0 && iy < in_h;
+      lp_load_row8<T>(xin + (long)(rok ? iy : 0) * in_w + x0, rok, x0 > 0, x0 + 8 < in_w, v[dy]);
+    }
+    T* op = out + pl * (long)(4 * in_h * in_w) + (long)(2 * yy) * out_w + 2 * x0;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      T pk[16];
+#pragma unroll
+      for (int px = 0; px < 8; ++px)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          float acc = 0.f;
+#pragma unroll
+          for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              const int i = a + 2 * ii, j = b + 2 * jj;
+              acc = fmaf(v[(a + i) / 2][px + (b + j) / 2], kf[i][j], acc);
+            }
+          pk[2 * px + b] = from_f<T>(acc);
+        }
+      uint4* dst = reinterpret_cast<uint4*>(op + (long)a * out_w);
+      dst[0] = reinterpret_cast<const uint4*>(pk)[0];
+      dst[1] = reinterpret_cast<const uint4*>(pk)[1];
+    }
+  }
+}
+
 template <typename T>
 static int launch_upfirdn_lp(const void* x, const float* k, void* out, long planes, const LpParams& p, cudaStream_t stream) {
   // band of output rows per CTA such that the staged input rows fit: rows_in <= (band*down + kh) / up + 2
+  const T* xi0 = (const T*)x;
+  T* oo0 = (T*)out;
+  const bool aligned = (p.in_w % 8 == 0) && (((uintptr_t)x & 15) == 0) && (((uintptr_t)out & 15) == 0);
+  if (aligned && p.kh == 4 && p.kw == 4 && p.up == 1 && p.down == 2 && p.pad0 == 1 && (p.in_h % 2 == 0) && p.out_h == p.in_h / 2 && p.out_w == p.in_w / 2) {
+    const long total = planes * ((p.out_h + 3) / 4) * (p.in_w / 8);
+    long blocks = (total + 255) / 256;
+    if (blocks > 148L * 32) blocks = 148L * 32;
+    lp_k4_down2_kernel<T><<<(int)blocks, 256, 0, stream>>>(xi0, k, oo0, planes, p.in_h, p.in_w, p.out_h, p.out_w);
+    return DDG_OK;
+  }
+  if (aligned && p.kh == 4 && p.kw == 4 && p.up == 2 && p.down == 1 && p.pad0 == 2 && p.out_h == 2 * p.in_h && p.out_w == 2 * p.in_w) {
+    const long total = planes * p.in_h * (p.in_w / 8);
+    long blocks = (total + 255) / 256;
+    if (blocks > 148L * 32) blocks = 148L * 32;
+    lp_k4_up2_kernel<T><<<(int)blocks, 256, 0, stream>>>(xi0, k, oo0, planes, p.in_h, p.in_w);
+    return DDG_OK;
+  }
   const int rows_cap = kLpCap / p.in_w;
   int band = ((rows_cap - 2) * p.up - p.kh) / p.down;
   if (band < 1) return DDG_ERR_UNSUPPORTED;

@@ -121,11 +121,13 @@ def test_sixteen_bit_operator_surface(dtype, tol):
     g = torch.Generator().manual_seed(3)
     x = torch.randn(4, 32, 16, 16, generator=g).to(DEV)
     xl = x.to(dtype)
-    for fn in (lambda t: upsample_2d(t, (1, 3, 3, 1), factor=2), lambda t: downsample_2d(t, (1, 3, 3, 1), factor=2)):
-        ref = fn(xl.float())
-        got = fn(xl)
-        assert got.dtype == dtype and got.shape == ref.shape
-        assert float((got.float() - ref).norm() / ref.norm()) < tol
+    # 16 x 16 (width % 8 == 0): the register-tiled 16-bit fast paths; 20 x 12: the staged general kernel
+    for xin in (xl, torch.randn(3, 8, 20, 12, generator=g).to(DEV).to(dtype), torch.randn(2, 4, 64, 64, generator=g).to(DEV).to(dtype)):
+        for fn in (lambda t: upsample_2d(t, (1, 3, 3, 1), factor=2), lambda t: downsample_2d(t, (1, 3, 3, 1), factor=2)):
+            ref = fn(xin.float())
+            got = fn(xin)
+            assert got.dtype == dtype and got.shape == ref.shape
+            assert float((got.float() - ref).norm() / ref.norm()) < tol
     k = torch.tensor([[1., 2., 1.], [2., 4., 2.], [1., 2., 1.]], device=DEV) / 16
     xr = xl.clone().requires_grad_(True)
     xf = xl.float().requires_grad_(True)
