@@ -27,8 +27,15 @@ import sys
 import threading
 import time
 
-# stdout carries exactly one JSON line: anything NCCL wants to say (its version banner under NCCL_DEBUG=VERSION / INFO) goes to stderr
-os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+# stdout carries exactly one JSON line.  Libraries print there too (NCCL's version banner comes out on file descriptor 1 of every rank),
+# so the real stdout is kept on a private descriptor for the result line and descriptor 1 is pointed at stderr for everything else.
+sys.stdout.flush()
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit_result(line):
+    os.write(_RESULT_FD, (json.dumps(line) + '\n').encode())
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, 'denoising-diffusion-gan_b200')
@@ -266,7 +273,7 @@ def run_reference(args):
         e = cpu_train_entry(16)
         line['train'] = {'metric': 'cifar10_train_samples_per_sec', 'value': e['value'], 'unit': 'samples/s',
                          'config': train_config(16), 'cpu_baseline': e}
-    print(json.dumps(line), flush=True)
+    emit_result(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -701,7 +708,7 @@ def run_b200(args):
             e = cpu_train_entry(16)
             (line['train'] if wl == 'all' else line)['cpu_baseline'] = e
     if ctx.rank == 0 and line is not None:
-        print(json.dumps(line), flush=True)
+        emit_result(line)
     if ctx.world > 1:
         dbg = os.environ.get('DDG_BENCH_DEBUG')
         if dbg:
