@@ -237,6 +237,7 @@ constexpr int kThreads = (kProdWarps + 2) * 32;   // one tile per CTA: the produ
 // (warp % 4 = TMEM lane quadrant).  Registers are moved from WG2 to the producers with setmaxnreg.
 constexpr int kThreadsPersist = 16 * 32;
 constexpr int kEpiWarp0 = 12;
+constexpr int kEpiSlotBytes = 12 * 64 * 4;         // per-warp bias / add-vector staging slots of the epilogue
 constexpr int kRegsProd = 168, kRegsUtil = 40, kRegsEpi = 128;   // 256*168 + 128*40 + 128*128 = 64512 <= 65536
 
 template <int MSUB, int NT, int KB, int PREC>
@@ -303,6 +304,7 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
   const int a_plane = KCH * p.win_pitch;          // bytes of one A plane
   const int a_stage = a_plane * NPL;
   uint8_t* sA = sB + NSB * Cfg::B_STAGE;
+  float* epi_slots = reinterpret_cast<float*>(sA + NSA * a_stage);   // 12 x 64 floats: one slot per epilogue-capable warp (see run_epilogue)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -364,8 +366,24 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
   // quad: TMEM lane quadrant of the calling warp; the warp handles column chunks half0, half0 + hstep, ...
   // it: tile iteration of this CTA (selects the accumulator set and the barrier parity).
   // wait_acc = false: the caller has already established that the tile's MMAs completed (see the producers' helper call)
-  auto run_epilogue = [&](int it, int quad, int half0, int hstep, bool release, bool wait_acc) {
+  // eslot: 64 floats of shared memory private to the calling warp.  The per-channel bias and the per-(sample, channel) add vector of a
+  // 32-column unit are fetched one unit ahead (one channel per lane, in flight during the previous unit -- the first one during the end of
+  // the mainloop) and broadcast to the row-per-lane layout through the slot: the eight dependent 128-bit global loads per operand that
+  // used to follow every tcgen05.ld exposed an L2 round trip (1-2k cycles under the producers' load) per unit.
+  auto run_epilogue = [&](int it, int quad, int half0, int hstep, bool release, bool wait_acc, float* eslot) {
     const int ab = PERSIST ? (it & 1) : 0;
+    constexpr int CW = (NT >= 64) ? 32 : 16;         // columns per tcgen05.ld
+    constexpr int NCHUNK = NT / CW;
+    float pb = 0.f, pa = 0.f;
+    auto prefetch = [&](int u) {
+      const int c0 = ntile * NT + (u % NCHUNK) * CW;
+      pb = 0.f; pa = 0.f;
+      if (CW == 32 && c0 + CW <= p.Cout) {
+        if (p.bias) pb = __ldg(p.bias + c0 + lane);
+        if (p.addvec && p.tile2d) pa = __ldg(p.addvec + (size_t)t2_n * p.addvec_stride + c0 + lane);
+      }
+    };
+    if (CW == 32 && half0 < MSUB * NCHUNK) prefetch(half0);
     if (wait_acc) mbar_wait(accFull(ab), PERSIST ? ((it >> 1) & 1) : 0);
     tc_fence_after();
     // split-K: ranks 0 .. ksplit-2 only park their partial accumulators; the last rank (highest block index of the tile, so that
@@ -379,8 +397,6 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
       }
       __syncwarp();
     }
-    constexpr int CW = (NT >= 64) ? 32 : 16;         // columns per tcgen05.ld
-    constexpr int NCHUNK = NT / CW;
     // work units = (sub-tile, column chunk) pairs, dealt round-robin to the warps that share this lane quadrant
     int sub_prev = -1;
     bool valid = false; int n = 0, h = 0, w = 0;
@@ -409,6 +425,12 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
         float v[CW];
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(ab * ACC_COLS + sub * NT + ck * CW);
         if (CW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+        if (CW == 32) {
+          __syncwarp();                                  // the previous unit has been read out of the slot
+          eslot[lane] = pb; eslot[32 + lane] = pa;
+          __syncwarp();
+          if (u + hstep < MSUB * NCHUNK) prefetch(u + hstep);
+        }
         tmem_ld_wait();
         if (sk_writer || sk_reduce) {
           const size_t prow = (size_t)(sub * 128 + quad * 32 + lane) * NT + ck * CW;   // thread = accumulator row: 128 contiguous bytes
@@ -433,18 +455,19 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
           if (full) {
             // vectorised per-channel bias and per-(sample, channel) add (Dense_0(temb) / dense_t1)
             if (p.bias) {
-              const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
               for (int j = 0; j < CW / 4; ++j) {
-                const float4 b = __ldg(b4 + j);
+                const float4 b = (CW == 32) ? *reinterpret_cast<const float4*>(eslot + 4 * j)
+                                            : __ldg(reinterpret_cast<const float4*>(p.bias + col0) + j);
                 v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
               }
             }
             if (p.addvec) {
+              const bool staged = (CW == 32) && p.tile2d;     // one sample per tile: the add vector came through the slot
               const float4* a4 = reinterpret_cast<const float4*>(p.addvec + (size_t)n * p.addvec_stride + col0);
 #pragma unroll
               for (int j = 0; j < CW / 4; ++j) {
-                const float4 b = __ldg(a4 + j);
+                const float4 b = staged ? *reinterpret_cast<const float4*>(eslot + 32 + 4 * j) : __ldg(a4 + j);
                 v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
               }
             }
@@ -787,7 +810,7 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
       const long long t_prod1 = DDG_CLK();
       mbar_wait(accFull(0), 0);
       const long long t_epi0 = DDG_CLK();
-      run_epilogue(0, warp & 3, warp >> 2, 2, true, true);
+      run_epilogue(0, warp & 3, warp >> 2, 2, true, true, epi_slots + warp * 64);
       if (prof_on && tid == 0) {
         p.prof[0] = t_prod1 - t_prod0;   // producer loop total
         p.prof[1] = w_emptyA;            // ... of which waiting for a free A stage
@@ -808,7 +831,7 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
     // last tile -- has completed, which is exactly the condition for reading the accumulators.
     if (PERSIST && it > 0) {
       mbar_wait(emptyA(last_st), last_ph);
-      run_epilogue(it - 1, warp & 3, 1 + (warp >> 2), 3, false, false);
+      run_epilogue(it - 1, warp & 3, 1 + (warp >> 2), 3, false, false, epi_slots + warp * 64);
     }
   } else if (warp < kEpiWarp0) {
     // WG2: the two single-thread roles (+ two idle warps in the persistent layout); their registers go to the producers
@@ -960,7 +983,7 @@ __global__ void __launch_bounds__(PERSIST ? kThreadsPersist : kThreads, 1) conv_
       set_tile(tile);
       const bool last = tile + tile_stride >= tile_end;
       { const long long tw = DDG_CLK(); mbar_wait(accFull(it & 1), (it >> 1) & 1); w_accF += DDG_CLK() - tw; }
-      run_epilogue(it, warp & 3, 0, last ? 3 : 1, true, true);
+      run_epilogue(it, warp & 3, 0, last ? 3 : 1, true, true, epi_slots + (8 + warp - kEpiWarp0) * 64);
     }
     if (PROF && p.prof != nullptr && blockIdx.x == gridDim.x / 2 && warp == kEpiWarp0 && lane == 0) {
       p.prof[11] = DDG_CLK() - t_e0;   // epilogue warps: whole tile loop
@@ -1059,7 +1082,7 @@ template <int MSUB, int NT, int KB, int PREC, bool PERSIST = false, bool PROF = 
 static int launch_conv(ConvDev& d, int n_tiles, cudaStream_t stream) {
   using Cfg = ConvCfg<MSUB, NT, KB, PREC>;
   const size_t a_stage = (size_t)Cfg::NPL * Cfg::KCH * d.win_pitch;
-  const size_t fixed = 256 + (size_t)Cfg::NSB * Cfg::B_STAGE;
+  const size_t fixed = 256 + (size_t)Cfg::NSB * Cfg::B_STAGE + kEpiSlotBytes;
   if (fixed + 2 * a_stage > 227 * 1024) { ddg_set_last_error("conv_tc: shared memory budget exceeded"); return DDG_ERR_UNSUPPORTED; }
   // A ring: as deep as the budget allows, up to 4 stages (1-tap K segments consume a stage in ~12 MMAs: two stages cannot hide the
   // load -> convert -> store latency of the producers)
