@@ -12,6 +12,7 @@ import torch.distributed as dist
 import torch.nn.functional as F
 
 from . import diffusion
+from . import ops
 
 
 def broadcast_params(params, src=0, modules=()):
@@ -270,6 +271,9 @@ class Trainer:
         # capturable=True keeps the Adam step counters on the device so that the whole step can be a CUDA graph
         cap = torch.device(device).type == 'cuda'
         self.fused_optim = fused_optim and cap
+        # conv / FIR outputs of the training graphs from ops.FRAME_POOL (no per-tensor border clears); DDG_TRAIN_FRAME_POOL=0 disables
+        import os as _os
+        self.frame_pool = cap and _os.environ.get('DDG_TRAIN_FRAME_POOL', '1') == '1'
         use_ema = bool(getattr(args, 'use_ema', True))
         ema_decay = _arg(args, ('ema_decay',), 0.9999) if use_ema else 0.0
         self.distributed = distributed and dist.is_initialized() and dist.get_world_size() > 1
@@ -387,10 +391,13 @@ class Trainer:
         from . import train_graph
         # with the flat arenas every parameter owns its .grad for good: let the wgrad / bias-sum kernels accumulate into it
         train_graph.ACCUM['on'] = self.fused_optim
+        if self.frame_pool:
+            ops.FRAME_POOL.begin_step()      # activations of this step come from the persistent frame-preserving pool
         try:
             out = self._step(real_data, global_step, noise)
         finally:
             train_graph.ACCUM['on'] = False
+            ops.FRAME_POOL.end_step()
         if not self._packs_frozen:
             # the first step recorded every weight pack of both networks; from now on one launch per network forward
             train_graph.freeze_packs(self.netG)

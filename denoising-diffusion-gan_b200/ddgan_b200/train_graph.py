@@ -158,7 +158,7 @@ def _conv_forward(x, w, bias, addvec, sp, res=None, w_ref=None):
         out = torch.zeros(sp.n, sp.cout, sp.hout, sp.wout, device=x.device)
         mode, out_c = ops.OUT_NCHW, 0
     else:
-        out = ops.alloc_pnhwc(sp.n, sp.hout, sp.wout, sp.cpad_out, x.device, full=(sp.cout != sp.cpad_out))
+        out = ops.alloc_pnhwc(sp.n, sp.hout, sp.wout, sp.cpad_out, x.device, full=(sp.cout != sp.cpad_out), pooled=True)
         mode, out_c = ops.OUT_PNHWC, sp.cpad_out
     ops.conv2d_fused(cw, [ops.conv_src(x, sp.cpad_in, sp.taps)], sp.n, sp.hout, sp.wout, out, out_mode=mode, out_c=out_c,
                      hp=sp.hp, wp=sp.wp, bias=bias, addvec=(addvec[0] if addvec is not None else None),
@@ -265,7 +265,7 @@ class DgradFn(Function):
         dye = _embed(dy, sp.hp, sp.wp).contiguous()
         cy = dye.shape[-1]
         cw = _packed(w, w_ref, 'dgrad', sp, dy.device, cy=cy)
-        dx = ops.alloc_pnhwc(sp.n, sp.hp - 2, sp.wp - 2, sp.cpad_in, dy.device, full=False)
+        dx = ops.alloc_pnhwc(sp.n, sp.hp - 2, sp.wp - 2, sp.cpad_in, dy.device, full=False, pooled=True)
         taps = [(-dr, -ds) for dr, ds in sp.taps]
         ops.conv2d_fused(cw, [ops.conv_src(dye, cy, taps)], sp.n, sp.hp - 2, sp.wp - 2, dx, out_scale=sp.out_scale,
                          splitk_ws=_splitk_ws(dy.device))
@@ -380,7 +380,7 @@ class FirFn(Function):
         x = x.contiguous()
         n, hp, wp, c = x.shape
         if mode == 1:
-            out = ops.alloc_pnhwc(n, 2 * (hp - 2), 2 * (wp - 2), c, x.device, full=False)
+            out = ops.alloc_pnhwc(n, 2 * (hp - 2), 2 * (wp - 2), c, x.device, full=False, pooled=True)
         elif mode == 2:
             out = ops.alloc_pnhwc(n, (hp - 2) // 2, (wp - 2) // 2, c, x.device, full=False)
         elif mode == 3:
