@@ -231,7 +231,10 @@ class FramePool:
         if i == len(lst):
             lst.append(make())
         self.cur[key] = i + 1
-        return lst[i]
+        # a fresh tensor object over the same storage every time: the object handed out last step carries that step's autograd
+        # history and hook table (a hook registered on it again would never reach the new grad_fn: Tensor.register_hook attaches
+        # the table to the node only when it creates it -- seen as the data-parallel early all-reduce not firing from step 2 on)
+        return lst[i].detach()
 
     def clear(self):
         self.bufs, self.cur = {}, {}

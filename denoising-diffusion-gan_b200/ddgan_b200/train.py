@@ -271,15 +271,12 @@ class Trainer:
         # capturable=True keeps the Adam step counters on the device so that the whole step can be a CUDA graph
         cap = torch.device(device).type == 'cuda'
         self.fused_optim = fused_optim and cap
-        # conv / FIR outputs of the training graphs from ops.FRAME_POOL (no per-tensor border clears); DDG_TRAIN_FRAME_POOL=0 disables.
-        # Single-process training only: with the pool on, tests/test_multigpu_gpu.py (two NCCL ranks, side-stream all-reduces) ended
-        # a real update with rank-dependent parameters -- cause not established, so data-parallel runs keep the per-tensor clears.
+        # conv / FIR outputs of the training graphs from ops.FRAME_POOL (no per-tensor border clears); DDG_TRAIN_FRAME_POOL=0 disables
         import os as _os
         self.frame_pool = cap and _os.environ.get('DDG_TRAIN_FRAME_POOL', '1') == '1'
         use_ema = bool(getattr(args, 'use_ema', True))
         ema_decay = _arg(args, ('ema_decay',), 0.9999) if use_ema else 0.0
         self.distributed = distributed and dist.is_initialized() and dist.get_world_size() > 1
-        self.frame_pool = self.frame_pool and not self.distributed
         self.world = dist.get_world_size() if self.distributed else 1
         if self.distributed:
             broadcast_params(netG.parameters(), modules=(netG,))
