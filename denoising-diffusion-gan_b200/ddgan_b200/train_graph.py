@@ -382,7 +382,7 @@ class FirFn(Function):
         if mode == 1:
             out = ops.alloc_pnhwc(n, 2 * (hp - 2), 2 * (wp - 2), c, x.device, full=False, pooled=True)
         elif mode == 2:
-            out = ops.alloc_pnhwc(n, (hp - 2) // 2, (wp - 2) // 2, c, x.device, full=False)
+            out = ops.alloc_pnhwc(n, (hp - 2) // 2, (wp - 2) // 2, c, x.device, full=False, pooled=True)
         elif mode == 3:
             out = torch.zeros(n, (hp - 2) // 2 + 3, (wp - 2) // 2 + 3, 4 * c, device=x.device)
         else:
