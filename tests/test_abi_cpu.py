@@ -58,3 +58,51 @@ def test_ops_refuse_cpu_tensors():
     from ddgan_b200 import ops
     with pytest.raises(RuntimeError):
         ops.upfirdn2d_raw(torch.zeros(1, 4, 4), torch.ones(2, 2), 1, 1, 1, 1, 0, 0, 0, 0)
+
+
+def test_frame_pool_hands_out_fresh_tensor_objects():
+    """ops.FramePool (training graphs inside Trainer.step): one cursor per shape rewound every step, distinct buffers within a step,
+    the same storage for the same call of the next step -- and a NEW tensor object every time.  Reusing the object itself would keep
+    last step's autograd history and hook table: a hook registered on it again never reaches the new grad_fn (that is how the
+    data-parallel early all-reduce stopped firing from the second step on; found by tests/test_multigpu_gpu.py)."""
+    import torch
+    from ddgan_b200 import ops
+    pool = ops.FramePool()
+    made = []
+
+    def make():
+        made.append(torch.zeros(2, 3))
+        return made[-1]
+    fired = []
+    ptrs = []
+    for step in range(3):
+        pool.begin_step()
+        a = pool.get('k', make)
+        b = pool.get('k', make)
+        pool.end_step()
+        assert a.data_ptr() != b.data_ptr()                       # distinct within a step
+        ptrs.append((a.data_ptr(), b.data_ptr()))
+        assert a.grad_fn is None and not a.requires_grad            # no history carried over
+    # the way train_graph uses the pool: a custom Function fetches its output buffer inside forward, the caller hooks the output.
+    # (With the stored object itself returned, only the first step's hook fires.)
+    class Fill(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, w):
+            out = pool.get('f', make)
+            out.copy_(w)
+            return out
+
+        @staticmethod
+        def backward(ctx, g):
+            return g
+    for step in range(3):
+        pool.begin_step()
+        w = torch.ones(2, 3, requires_grad=True)
+        h = Fill.apply(w)
+        h.register_hook(lambda g, s=step: fired.append(s))
+        (h * 2).sum().backward()
+        pool.end_step()
+        assert torch.equal(w.grad, torch.full((2, 3), 2.0))
+    assert len(made) == 3 and ptrs[0] == ptrs[1] == ptrs[2]         # same storage step after step (2 of key 'k', 1 of key 'f')
+    assert fired == [0, 1, 2]
+    assert not pool.active
