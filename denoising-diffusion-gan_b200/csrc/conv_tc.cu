@@ -26,6 +26,11 @@
 //     are more tiles than SMs -- the PERSIST variant: 16 warps, every CTA walks tiles b, b + grid, ..., two accumulator
 //     sets in TMEM and four dedicated epilogue warps overlap the epilogue of tile i with the mainloop of tile i + 1,
 //     setmaxnreg moves registers from the single-thread roles to the producer warpgroups.
+//   * Prologue-free K segments that come with pre-split bf16 planes ([plane][N][C/8][H+2][W+2][8], written by the producing conv's
+//     epilogue or ddg_split_planes) are fetched by the TMA engine (cp.async.bulk.tensor.4d, one 160-byte box row per halo-window
+//     row) straight into the A ring; the producer warps only keep the barrier count for those stages.
+//   * Small spatial levels (a few dozen one-tile CTAs): SPLITK instantiations run 2 or 4 CTAs per output tile over disjoint K
+//     ranges; partial accumulators meet in a caller workspace (ddg_conv_desc.splitk_ws), the last rank of a tile reduces.
 #include <cstdlib>
 #include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
 #include "common.cuh"
